@@ -1,0 +1,860 @@
+// engine.cu — C-ABI (include/fastllama_b200.h) over the sm_100a kernels in kernels.cuh.
+//
+// One fl_engine per GPU: packed weights, fp32 KV cache, pre-allocated workspace, one CUDA graph per KV slot
+// that replays the whole decode step (embedding -> n_layers x {QKV, attention, Wo, W1/W3+SwiGLU, W2} ->
+// classifier -> argmax + state advance).  No allocation and no host<->device traffic per token unless the
+// caller asks for logits.  There is no CPU path: every entry point needs a CUDA device.
+#include "../../include/fastllama_b200.h"
+#include "kernels.cuh"
+
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <type_traits>
+#include <vector>
+
+using namespace fl;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int set_err(fl_engine* e, int code, const char* fmt, ...);
+
+#define CK(e, call)                                                                                         \
+    do {                                                                                                    \
+        cudaError_t _st = (call);                                                                           \
+        if (_st != cudaSuccess)                                                                             \
+            return set_err(e, FL_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_st), __FILE__, __LINE__); \
+    } while (0)
+
+struct PackedMat {
+    uint8_t* d = nullptr;
+    int M = 0;          // logical rows (hidden for the W1/W3 stream)
+    int K = 0;
+    int n_tiles = 0;    // row tiles in the stream
+    int nkb = 0;
+    size_t bytes = 0;
+};
+
+}  // namespace
+
+struct fl_engine {
+    fl_config c{};
+    int device = 0;
+    int n_sms = 148;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    // weights
+    float* emb = nullptr;
+    float* att_norm = nullptr;
+    float* ffn_norm = nullptr;
+    float* out_norm = nullptr;
+    std::vector<PackedMat> qkv, wo, w13, w2;
+    PackedMat cls;
+    std::vector<uint8_t> have;          // [kind][layer]
+    uint8_t* staging = nullptr;
+    size_t staging_bytes = 0;
+    // runtime
+    float *x1 = nullptr, *qkv_buf = nullptr, *attn = nullptr, *hd = nullptr, *logits = nullptr;
+    float *tap_qkv = nullptr, *tap_norm = nullptr;
+    float *k_cache = nullptr, *v_cache = nullptr;
+    float* rope = nullptr;
+    SeqState* states = nullptr;
+    int* out_tokens = nullptr;
+    int out_cap = 0;
+    int* in_tokens = nullptr;
+    int in_cap = 0;
+    int* argmax_dev = nullptr;
+    int* h_tokens = nullptr;            // pinned
+    float* h_logits = nullptr;          // pinned
+    int* h_argmax = nullptr;            // pinned
+    std::vector<cudaGraphExec_t> graphs;
+    bool finalized = false;
+    int64_t launches = 0;
+    int kernels_per_step = 0;
+    // NCCL (dlopen'ed; only when a communicator is bound)
+    void* nccl_lib = nullptr;
+    void* nccl_comm = nullptr;
+    int rank = 0, world = 1;
+    int* ag_send = nullptr;
+    int* ag_recv = nullptr;
+};
+
+namespace {
+
+int set_err(fl_engine* e, int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    if (e) e->err = buf;
+    return code;
+}
+
+inline int es_of(int qt) { return qt == FL_Q_INT8 ? 1 : 2; }
+inline int unit_bytes(int qt, int gs) {
+    const int lb = 64 * es_of(qt), gpl = 64 / gs;
+    return 32 * lb + 32 * gpl * 4;
+}
+
+int alloc_packed(fl_engine* e, PackedMat& m, int rows_in_stream, int logical_rows, int K) {
+    m.M = logical_rows;
+    m.K = K;
+    m.n_tiles = ceil_div(rows_in_stream, 4);
+    m.nkb = ceil_div(K, kKBlockElems);
+    m.bytes = (size_t)m.n_tiles * m.nkb * unit_bytes(e->c.quant_type, e->c.group_size);
+    CK(e, cudaMalloc(&m.d, m.bytes));
+    CK(e, cudaMemsetAsync(m.d, 0, m.bytes, e->stream));
+    return FL_OK;
+}
+
+// dispatch helpers over (quant type, group size)
+template <typename F>
+int dispatch_q(int qt, int gs, F&& f) {
+    if (qt == FL_Q_INT8 && gs == 64) return f(std::integral_constant<int, Q_INT8>{}, std::integral_constant<int, 64>{});
+    if (qt == FL_Q_INT8 && gs == 32) return f(std::integral_constant<int, Q_INT8>{}, std::integral_constant<int, 32>{});
+    if (qt == FL_Q_INT16 && gs == 64) return f(std::integral_constant<int, Q_INT16>{}, std::integral_constant<int, 64>{});
+    return FL_ERR_UNSUPPORTED;
+}
+
+size_t gemv_smem_bytes(int qt, int gs, int K, bool with_xf) {
+    const int nkb = ceil_div(K, kKBlockElems);
+    return (size_t)nkb * kKBlockElems * es_of(qt) + (size_t)nkb * 8 * (64 / gs) * 4 + (with_xf ? (size_t)K * 4 : 0);
+}
+
+template <int PRO, int EPI>
+int launch_gemv(fl_engine* e, int qt, int gs, const GemvArgs& a, int grid, cudaStream_t st) {
+    const size_t smem = gemv_smem_bytes(qt, gs, a.K, PRO == PRO_RMS_QUANT);
+    return dispatch_q(qt, gs, [&](auto QT, auto GS) -> int {
+        auto kern = gemv_kernel<decltype(QT)::value, decltype(GS)::value, PRO, EPI>;
+        if (smem > 48 * 1024) {
+            cudaError_t st2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (st2 != cudaSuccess) return set_err(e, FL_ERR_CUDA, "cudaFuncSetAttribute(gemv): %s", cudaGetErrorString(st2));
+        }
+        kern<<<grid, kThreads, smem, st>>>(a);
+        cudaError_t st3 = cudaGetLastError();
+        if (st3 != cudaSuccess) return set_err(e, FL_ERR_CUDA, "gemv launch: %s", cudaGetErrorString(st3));
+        return FL_OK;
+    });
+}
+
+size_t attn_smem_bytes(int hs, int max_seq) {
+    return (size_t)(3 * hs + 32 + 2 * kVChunk * hs + max_seq) * sizeof(float);
+}
+
+int launch_attn(fl_engine* e, int hs, const AttnArgs& a, int max_seq, cudaStream_t st) {
+    const size_t smem = attn_smem_bytes(hs, max_seq);
+    cudaError_t s1 = cudaSuccess;
+    if (hs == 128) {
+        s1 = cudaFuncSetAttribute(attn_decode_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (s1 == cudaSuccess) attn_decode_kernel<128><<<a.n_heads, kThreads, smem, st>>>(a);
+    } else if (hs == 64) {
+        s1 = cudaFuncSetAttribute(attn_decode_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (s1 == cudaSuccess) attn_decode_kernel<64><<<a.n_heads, kThreads, smem, st>>>(a);
+    } else {
+        return set_err(e, FL_ERR_UNSUPPORTED, "head_size %d not supported (64 or 128)", hs);
+    }
+    if (s1 != cudaSuccess) return set_err(e, FL_ERR_CUDA, "cudaFuncSetAttribute(attn): %s", cudaGetErrorString(s1));
+    s1 = cudaGetLastError();
+    if (s1 != cudaSuccess) return set_err(e, FL_ERR_CUDA, "attn launch: %s", cudaGetErrorString(s1));
+    return FL_OK;
+}
+
+// RoPE table exactly as rope_v2 walks it (tf_operators.cpp:367-395): theta_scale = powf(10000, -2/n),
+// theta_0 = pos, theta_{k+1} = theta_k * theta_scale in float, glibc sincosf.
+void build_rope_table(std::vector<float>& tab, int n_pos, int hs) {
+    tab.resize((size_t)n_pos * hs);
+    const float theta_scale = powf(10000.0f, -2.0f / (float)hs);
+    for (int p = 0; p < n_pos; ++p) {
+        float theta = (float)p;
+        for (int i = 0; i < hs; i += 2) {
+            float s, c;
+            sincosf(theta, &s, &c);
+            tab[(size_t)p * hs + i] = c;
+            tab[(size_t)p * hs + i + 1] = s;
+            theta *= theta_scale;
+        }
+    }
+}
+
+__global__ void dequant_rows_kernel(const uint8_t* q, const float* s, float* out, size_t n, int gs, int qt) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int v = (qt == FL_Q_INT8) ? (int)reinterpret_cast<const int8_t*>(q)[i] : (int)reinterpret_cast<const int16_t*>(q)[i];
+        out[i] = __fmul_rn(__int2float_rn(v), s[i / gs]);      // quant_operators.cpp:61
+    }
+}
+
+int gemv_grid(const fl_engine* e, int n_tasks) {
+    const int full = e->n_sms * 2;
+    const int need = ceil_div(n_tasks, kWarps);
+    return need < full ? (need < 1 ? 1 : need) : full;
+}
+
+// enqueue one decode step for `slot` on `st` (captured into a graph, or launched directly)
+int enqueue_step(fl_engine* e, int slot, cudaStream_t st, int* n_kernels) {
+    const fl_config& c = e->c;
+    const int qt = c.quant_type, gs = c.group_size;
+    const int kv_dim = c.head_size * c.n_kv_heads;
+    SeqState* state = e->states + slot;
+    int nk = 0;
+    embed_kernel<<<4, 256, 0, st>>>(e->emb, &state->token, e->x1, c.dim);
+    ++nk;
+    const size_t cache_per_layer = (size_t)c.n_kv_heads * c.max_seq_len * c.head_size;
+    const size_t cache_per_slot = cache_per_layer * c.n_layers;
+    for (int l = 0; l < c.n_layers; ++l) {
+        GemvArgs g{};
+        // x2 = rmsnorm(x1); qkv = Wqkv * quantize(x2)            (transformer.cpp:132-135, :386-395)
+        g.w = e->qkv[l].d; g.M = e->qkv[l].M; g.K = c.dim; g.n_tasks = e->qkv[l].n_tiles; g.nkb = e->qkv[l].nkb;
+        g.in = e->x1; g.gain = e->att_norm + (size_t)l * c.dim; g.out = e->qkv_buf; g.tap = nullptr;
+        int rc = launch_gemv<PRO_RMS_QUANT, EPI_STORE>(e, qt, gs, g, gemv_grid(e, g.n_tasks), st);
+        if (rc) return rc;
+        ++nk;
+        // RoPE, KV append, QK^T, softmax, .V                      (:136, :397-455)
+        AttnArgs a{};
+        a.qkv = e->qkv_buf;
+        a.k_cache = e->k_cache + slot * cache_per_slot + l * cache_per_layer;
+        a.v_cache = e->v_cache + slot * cache_per_slot + l * cache_per_layer;
+        a.rope = e->rope; a.pos_ptr = &state->pos; a.bs_ptr = &state->bs; a.out = e->attn;
+        a.tap_qkv = (l == c.n_layers - 1) ? e->tap_qkv : nullptr;
+        a.n_heads = c.n_heads; a.n_kv_heads = c.n_kv_heads; a.max_seq = c.max_seq_len;
+        a.attn_scale = 1.0f / sqrtf((float)c.head_size);
+        rc = launch_attn(e, c.head_size, a, c.max_seq_len, st);
+        if (rc) return rc;
+        ++nk;
+        // x1 += Wo * quantize(attn)                               (:138-139, :457-466)
+        g = GemvArgs{};
+        g.w = e->wo[l].d; g.M = c.dim; g.K = c.dim; g.n_tasks = e->wo[l].n_tiles; g.nkb = e->wo[l].nkb;
+        g.in = e->attn; g.out = e->x1;
+        rc = launch_gemv<PRO_QUANT, EPI_RESADD>(e, qt, gs, g, gemv_grid(e, g.n_tasks), st);
+        if (rc) return rc;
+        ++nk;
+        // hd = swiglu(W1 q, W3 q), q = quantize(rmsnorm(x1))      (:144-147, :468-483)
+        g = GemvArgs{};
+        g.w = e->w13[l].d; g.M = c.hidden_dim; g.K = c.dim; g.n_tasks = e->w13[l].n_tiles / 2; g.nkb = e->w13[l].nkb;
+        g.in = e->x1; g.gain = e->ffn_norm + (size_t)l * c.dim; g.out = e->hd;
+        rc = launch_gemv<PRO_RMS_QUANT, EPI_SWIGLU>(e, qt, gs, g, gemv_grid(e, g.n_tasks), st);
+        if (rc) return rc;
+        ++nk;
+        // x1 += W2 * quantize(hd)                                 (:149-150, :485-494)
+        g = GemvArgs{};
+        g.w = e->w2[l].d; g.M = c.dim; g.K = c.hidden_dim; g.n_tasks = e->w2[l].n_tiles; g.nkb = e->w2[l].nkb;
+        g.in = e->hd; g.out = e->x1;
+        rc = launch_gemv<PRO_QUANT, EPI_RESADD>(e, qt, gs, g, gemv_grid(e, g.n_tasks), st);
+        if (rc) return rc;
+        ++nk;
+    }
+    // logits = Wcls * quantize(rmsnorm(x1))                      (:154-160, :496-505)
+    GemvArgs g{};
+    g.w = e->cls.d; g.M = c.vocab_size; g.K = c.dim; g.n_tasks = e->cls.n_tiles; g.nkb = e->cls.nkb;
+    g.in = e->x1; g.gain = e->out_norm; g.out = e->logits; g.tap = e->tap_norm;
+    int rc = launch_gemv<PRO_RMS_QUANT, EPI_STORE>(e, qt, gs, g, gemv_grid(e, g.n_tasks), st);
+    if (rc) return rc;
+    ++nk;
+    argmax_kernel<<<1, 1024, 0, st>>>(e->logits, c.vocab_size, state, e->out_tokens + (size_t)slot * e->out_cap, e->out_cap,
+                                      e->argmax_dev + slot, 1);
+    ++nk;
+    (void)kv_dim;
+    cudaError_t s = cudaGetLastError();
+    if (s != cudaSuccess) return set_err(e, FL_ERR_CUDA, "step launch: %s", cudaGetErrorString(s));
+    if (n_kernels) *n_kernels = nk;
+    return FL_OK;
+}
+
+int run_step(fl_engine* e, int slot) {
+    if (e->c.flags & FL_FLAG_NO_GRAPH) {
+        int nk = 0;
+        int rc = enqueue_step(e, slot, e->stream, &nk);
+        e->launches += nk;
+        return rc;
+    }
+    if (!e->graphs[slot]) {
+        cudaGraph_t graph = nullptr;
+        CK(e, cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+        int nk = 0;
+        int rc = enqueue_step(e, slot, e->stream, &nk);
+        cudaError_t s = cudaStreamEndCapture(e->stream, &graph);
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (s != cudaSuccess) return set_err(e, FL_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(s));
+        e->kernels_per_step = nk;
+        s = cudaGraphInstantiate(&e->graphs[slot], graph, 0);
+        cudaGraphDestroy(graph);
+        if (s != cudaSuccess) return set_err(e, FL_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(s));
+    }
+    CK(e, cudaGraphLaunch(e->graphs[slot], e->stream));
+    e->launches += e->kernels_per_step;
+    return FL_OK;
+}
+
+}  // namespace
+
+namespace {
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(size_t n) { return cudaMalloc(&p, n ? n : 16) == cudaSuccess ? 0 : -1; }
+    template <typename T> T* as() { return reinterpret_cast<T*>(p); }
+};
+int need_device() {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) return set_err(nullptr, FL_ERR_CUDA, "no CUDA device (this library has no CPU path)");
+    return FL_OK;
+}
+#define CKO(call) CK(nullptr, call)
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+const char* fl_last_error(const fl_engine* e) { return e ? e->err.c_str() : g_last_error.c_str(); }
+
+int fl_create(const fl_config* cfg, int device, fl_engine** out) {
+    if (!cfg || !out) return set_err(nullptr, FL_ERR_INVALID, "fl_create: null argument");
+    *out = nullptr;
+    const fl_config& c = *cfg;
+    if (c.dim <= 0 || c.hidden_dim <= 0 || c.n_layers <= 0 || c.n_heads <= 0 || c.n_kv_heads <= 0 || c.vocab_size <= 0 ||
+        c.max_seq_len <= 0 || c.max_seqs <= 0)
+        return set_err(nullptr, FL_ERR_INVALID, "fl_create: non-positive dimension");
+    if (c.head_size * c.n_heads != c.dim || c.n_heads % c.n_kv_heads != 0)
+        return set_err(nullptr, FL_ERR_INVALID, "fl_create: head_size*n_heads != dim or n_heads %% n_kv_heads != 0");
+    if (c.head_size != 64 && c.head_size != 128)
+        return set_err(nullptr, FL_ERR_UNSUPPORTED, "fl_create: head_size must be 64 or 128");
+    if (!((c.quant_type == FL_Q_INT8 && (c.group_size == 64 || c.group_size == 32)) || (c.quant_type == FL_Q_INT16 && c.group_size == 64)))
+        return set_err(nullptr, FL_ERR_UNSUPPORTED, "fl_create: quant_type/group_size combination not supported");
+    if (c.dim % 64 || c.hidden_dim % 64)
+        return set_err(nullptr, FL_ERR_INVALID, "fl_create: dim and hidden_dim must be multiples of 64");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+        return set_err(nullptr, FL_ERR_CUDA, "fl_create: no CUDA device (this library has no CPU path)");
+    if (device < 0 || device >= ndev) return set_err(nullptr, FL_ERR_INVALID, "fl_create: device %d out of range", device);
+
+    fl_engine* e = new fl_engine();
+    e->c = c;
+    e->device = device;
+    auto fail = [&](int rc) { std::string m = e->err; fl_destroy(e); g_last_error = m; return rc; };
+#define CKF(call) do { int _rc = [&]() -> int { CK(e, call); return FL_OK; }(); if (_rc) return fail(_rc); } while (0)
+    CKF(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CKF(cudaGetDeviceProperties(&prop, device));
+    e->n_sms = prop.multiProcessorCount;
+    CKF(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+
+    const int L = c.n_layers, kv_dim = c.head_size * c.n_kv_heads;
+    e->have.assign((size_t)FL_T__COUNT * L, 0);
+    e->qkv.resize(L); e->wo.resize(L); e->w13.resize(L); e->w2.resize(L);
+    e->graphs.assign(c.max_seqs, nullptr);
+    CKF(cudaMalloc(&e->emb, (size_t)c.vocab_size * c.dim * 4));
+    CKF(cudaMalloc(&e->att_norm, (size_t)L * c.dim * 4));
+    CKF(cudaMalloc(&e->ffn_norm, (size_t)L * c.dim * 4));
+    CKF(cudaMalloc(&e->out_norm, (size_t)c.dim * 4));
+    for (int l = 0; l < L; ++l) {
+        int rc = alloc_packed(e, e->qkv[l], c.dim + 2 * kv_dim, c.dim + 2 * kv_dim, c.dim);
+        if (!rc) rc = alloc_packed(e, e->wo[l], c.dim, c.dim, c.dim);
+        if (!rc) rc = alloc_packed(e, e->w13[l], 2 * ceil_div(c.hidden_dim, 4) * 4, c.hidden_dim, c.dim);
+        if (!rc) rc = alloc_packed(e, e->w2[l], c.dim, c.dim, c.hidden_dim);
+        if (rc) return fail(rc);
+    }
+    { int rc = alloc_packed(e, e->cls, c.vocab_size, c.vocab_size, c.dim); if (rc) return fail(rc); }
+    const int es = es_of(c.quant_type);
+    size_t max_elems = (size_t)c.vocab_size * c.dim;
+    if ((size_t)c.hidden_dim * c.dim > max_elems) max_elems = (size_t)c.hidden_dim * c.dim;
+    e->staging_bytes = ((max_elems * es + 255) & ~(size_t)255) + max_elems / c.group_size * 4 + 256;
+    CKF(cudaMalloc(&e->staging, e->staging_bytes));
+
+    CKF(cudaMalloc(&e->x1, (size_t)c.dim * 4));
+    CKF(cudaMalloc(&e->qkv_buf, (size_t)(c.dim + 2 * kv_dim) * 4));
+    CKF(cudaMalloc(&e->attn, (size_t)c.dim * 4));
+    CKF(cudaMalloc(&e->hd, (size_t)c.hidden_dim * 4));
+    CKF(cudaMalloc(&e->logits, (size_t)c.vocab_size * 4));
+    CKF(cudaMalloc(&e->tap_qkv, (size_t)(c.dim + 2 * kv_dim) * 4));
+    CKF(cudaMalloc(&e->tap_norm, (size_t)c.dim * 4));
+    const size_t cache_elems = (size_t)c.max_seqs * L * c.n_kv_heads * c.max_seq_len * c.head_size;
+    CKF(cudaMalloc(&e->k_cache, cache_elems * 4));
+    CKF(cudaMalloc(&e->v_cache, cache_elems * 4));
+    CKF(cudaMemsetAsync(e->k_cache, 0, cache_elems * 4, e->stream));
+    CKF(cudaMemsetAsync(e->v_cache, 0, cache_elems * 4, e->stream));
+    CKF(cudaMalloc(&e->states, sizeof(SeqState) * c.max_seqs));
+    CKF(cudaMemsetAsync(e->states, 0, sizeof(SeqState) * c.max_seqs, e->stream));
+    e->out_cap = c.max_seq_len + 8;
+    CKF(cudaMalloc(&e->out_tokens, sizeof(int) * (size_t)e->out_cap * c.max_seqs));
+    e->in_cap = c.max_seq_len > 64 ? c.max_seq_len : 64;
+    CKF(cudaMalloc(&e->in_tokens, sizeof(int) * e->in_cap));
+    CKF(cudaMalloc(&e->argmax_dev, sizeof(int) * c.max_seqs));
+    CKF(cudaMalloc(&e->ag_send, sizeof(int) * 1024));
+    CKF(cudaMalloc(&e->ag_recv, sizeof(int) * 1024 * 16));
+    CKF(cudaMallocHost(&e->h_tokens, sizeof(int) * e->in_cap));
+    CKF(cudaMallocHost(&e->h_logits, sizeof(float) * c.vocab_size));
+    CKF(cudaMallocHost(&e->h_argmax, sizeof(int) * (c.max_seqs > 1024 ? c.max_seqs : 1024)));
+    CKF(cudaStreamSynchronize(e->stream));
+#undef CKF
+    *out = e;
+    return FL_OK;
+}
+
+void fl_destroy(fl_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    for (auto g : e->graphs) if (g) cudaGraphExecDestroy(g);
+    auto fr = [](void* p) { if (p) cudaFree(p); };
+    fr(e->emb); fr(e->att_norm); fr(e->ffn_norm); fr(e->out_norm);
+    for (auto& m : e->qkv) fr(m.d);
+    for (auto& m : e->wo) fr(m.d);
+    for (auto& m : e->w13) fr(m.d);
+    for (auto& m : e->w2) fr(m.d);
+    fr(e->cls.d); fr(e->staging);
+    fr(e->x1); fr(e->qkv_buf); fr(e->attn); fr(e->hd); fr(e->logits); fr(e->tap_qkv); fr(e->tap_norm);
+    fr(e->k_cache); fr(e->v_cache); fr(e->rope); fr(e->states); fr(e->out_tokens); fr(e->in_tokens); fr(e->argmax_dev);
+    fr(e->ag_send); fr(e->ag_recv);
+    if (e->h_tokens) cudaFreeHost(e->h_tokens);
+    if (e->h_logits) cudaFreeHost(e->h_logits);
+    if (e->h_argmax) cudaFreeHost(e->h_argmax);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    if (e->nccl_lib) dlclose(e->nccl_lib);
+    delete e;
+}
+
+int fl_upload(fl_engine* e, int kind, int layer, const void* q, const float* scales, int rows, int cols) {
+    if (!e || !q) return set_err(e, FL_ERR_INVALID, "fl_upload: null argument");
+    if (e->finalized) return set_err(e, FL_ERR_INVALID, "fl_upload: engine already finalized");
+    const fl_config& c = e->c;
+    if (kind < 0 || kind >= FL_T__COUNT) return set_err(e, FL_ERR_INVALID, "fl_upload: bad tensor kind %d", kind);
+    const bool per_layer = !(kind == FL_T_TOK_EMB || kind == FL_T_OUT_NORM || kind == FL_T_CLS);
+    if (layer < 0 || layer >= (per_layer ? c.n_layers : 1)) return set_err(e, FL_ERR_INVALID, "fl_upload: bad layer %d for kind %d", layer, kind);
+    CK(e, cudaSetDevice(e->device));
+    const int kv_dim = c.head_size * c.n_kv_heads;
+    int exp_rows = 0, exp_cols = 0;
+    switch (kind) {
+        case FL_T_TOK_EMB: case FL_T_CLS: exp_rows = c.vocab_size; exp_cols = c.dim; break;
+        case FL_T_ATT_NORM: case FL_T_FFN_NORM: case FL_T_OUT_NORM: exp_rows = 1; exp_cols = c.dim; break;
+        case FL_T_WQ: case FL_T_WO: exp_rows = c.dim; exp_cols = c.dim; break;
+        case FL_T_WK: case FL_T_WV: exp_rows = kv_dim; exp_cols = c.dim; break;
+        case FL_T_W1: case FL_T_W3: exp_rows = c.hidden_dim; exp_cols = c.dim; break;
+        case FL_T_W2: exp_rows = c.dim; exp_cols = c.hidden_dim; break;
+    }
+    if (rows != exp_rows || cols != exp_cols)
+        return set_err(e, FL_ERR_INVALID, "fl_upload: kind %d expects %dx%d, got %dx%d", kind, exp_rows, exp_cols, rows, cols);
+    const size_t n = (size_t)rows * cols;
+    const int qt = c.quant_type, gs = c.group_size, es = es_of(qt);
+
+    if (kind == FL_T_ATT_NORM || kind == FL_T_FFN_NORM || kind == FL_T_OUT_NORM) {
+        float* dst = kind == FL_T_ATT_NORM ? e->att_norm + (size_t)layer * c.dim
+                   : kind == FL_T_FFN_NORM ? e->ffn_norm + (size_t)layer * c.dim : e->out_norm;
+        CK(e, cudaMemcpy(dst, q, n * 4, cudaMemcpyHostToDevice));
+    } else if (kind == FL_T_TOK_EMB && scales == nullptr) {
+        CK(e, cudaMemcpy(e->emb, q, n * 4, cudaMemcpyHostToDevice));         // .flm keeps fp32 embedding rows
+    } else {
+        if (!scales) return set_err(e, FL_ERR_INVALID, "fl_upload: kind %d needs a scale table", kind);
+        float* d_scales = reinterpret_cast<float*>(e->staging + ((n * es + 255) & ~(size_t)255));
+        CK(e, cudaMemcpy(e->staging, q, n * es, cudaMemcpyHostToDevice));
+        CK(e, cudaMemcpy(d_scales, scales, n / gs * 4, cudaMemcpyHostToDevice));
+        if (kind == FL_T_TOK_EMB) {
+            // dequantised once here; the reference dequantises the row per token (transformer.cpp:117-118), same bits
+            dequant_rows_kernel<<<1024, 256, 0, e->stream>>>(e->staging, d_scales, e->emb, n, gs, qt);
+        } else {
+            PackedMat* m = nullptr;
+            int tile_offset = 0, tile_stride = 1;
+            switch (kind) {
+                case FL_T_WQ: m = &e->qkv[layer]; break;
+                case FL_T_WK: m = &e->qkv[layer]; tile_offset = c.dim / 4; break;
+                case FL_T_WV: m = &e->qkv[layer]; tile_offset = (c.dim + kv_dim) / 4; break;
+                case FL_T_WO: m = &e->wo[layer]; break;
+                case FL_T_W1: m = &e->w13[layer]; tile_stride = 2; break;
+                case FL_T_W3: m = &e->w13[layer]; tile_stride = 2; tile_offset = 1; break;
+                case FL_T_W2: m = &e->w2[layer]; break;
+                case FL_T_CLS: m = &e->cls; break;
+            }
+            const int n_tiles = ceil_div(rows, 4);
+            int rc = dispatch_q(qt, gs, [&](auto QT, auto GS) -> int {
+                pack_weights_kernel<decltype(QT)::value, decltype(GS)::value><<<2048, 256, 0, e->stream>>>(
+                    e->staging, d_scales, m->d, rows, cols, n_tiles, m->nkb, tile_stride, tile_offset);
+                return FL_OK;
+            });
+            if (rc) return set_err(e, rc, "fl_upload: unsupported quantisation");
+        }
+        CK(e, cudaGetLastError());
+        CK(e, cudaStreamSynchronize(e->stream));
+    }
+    e->have[(size_t)kind * c.n_layers + layer] = 1;
+    return FL_OK;
+}
+
+int fl_finalize(fl_engine* e) {
+    if (!e) return set_err(e, FL_ERR_INVALID, "fl_finalize: null engine");
+    if (e->finalized) return FL_OK;
+    const fl_config& c = e->c;
+    for (int k = 0; k < FL_T__COUNT; ++k) {
+        const bool per_layer = !(k == FL_T_TOK_EMB || k == FL_T_OUT_NORM || k == FL_T_CLS);
+        for (int l = 0; l < (per_layer ? c.n_layers : 1); ++l)
+            if (!e->have[(size_t)k * c.n_layers + l]) return set_err(e, FL_ERR_INVALID, "fl_finalize: tensor kind %d layer %d was never uploaded", k, l);
+    }
+    CK(e, cudaSetDevice(e->device));
+    const int hgs = c.n_heads / c.n_kv_heads;
+    std::vector<float> tab;
+    build_rope_table(tab, c.max_seq_len * hgs + 1, c.head_size);   // q positions reach pos + g*bs (GQA quirk)
+    CK(e, cudaMalloc(&e->rope, tab.size() * 4));
+    CK(e, cudaMemcpy(e->rope, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
+    if (e->staging) { cudaFree(e->staging); e->staging = nullptr; }
+    e->finalized = true;
+    return FL_OK;
+}
+
+int fl_forward(fl_engine* e, int seq_slot, const int32_t* tokens, int n_tokens, int pos, float* logits_out, int32_t* argmax_out) {
+    if (!e || !tokens) return set_err(e, FL_ERR_INVALID, "fl_forward: null argument");
+    if (!e->finalized) return set_err(e, FL_ERR_INVALID, "fl_forward: call fl_finalize first");
+    const fl_config& c = e->c;
+    if (seq_slot < 0 || seq_slot >= c.max_seqs) return set_err(e, FL_ERR_INVALID, "fl_forward: bad seq_slot %d", seq_slot);
+    if (n_tokens < 1 || n_tokens > e->in_cap || pos < 0 || pos + n_tokens > c.max_seq_len)
+        return set_err(e, FL_ERR_INVALID, "fl_forward: pos %d + n_tokens %d exceeds max_seq_len %d", pos, n_tokens, c.max_seq_len);
+    for (int i = 0; i < n_tokens; ++i)
+        if (tokens[i] < 0 || tokens[i] >= c.vocab_size) return set_err(e, FL_ERR_INVALID, "fl_forward: token id %d out of range", tokens[i]);
+    CK(e, cudaSetDevice(e->device));
+    memcpy(e->h_tokens, tokens, sizeof(int) * n_tokens);
+    CK(e, cudaMemcpyAsync(e->in_tokens, e->h_tokens, sizeof(int) * n_tokens, cudaMemcpyHostToDevice, e->stream));
+    // Prefill runs the tokens one position at a time: bit-identical to the reference's bs>1 forward, whose
+    // per-row arithmetic does not depend on the other rows (DESIGN.md "Prefill").
+    for (int i = 0; i < n_tokens; ++i) {
+        // n_out restarts at the last token of the call, so out_tokens[0] is the token sampled after the whole input
+        set_state_kernel<<<1, 1, 0, e->stream>>>(e->states + seq_slot, e->in_tokens, i, pos + i, n_tokens, i == n_tokens - 1);
+        e->launches += 1;
+        int rc = run_step(e, seq_slot);
+        if (rc) return rc;
+    }
+    if (logits_out) CK(e, cudaMemcpyAsync(e->h_logits, e->logits, sizeof(float) * c.vocab_size, cudaMemcpyDeviceToHost, e->stream));
+    if (argmax_out) CK(e, cudaMemcpyAsync(e->h_argmax, e->argmax_dev + seq_slot, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    if (logits_out) memcpy(logits_out, e->h_logits, sizeof(float) * c.vocab_size);
+    if (argmax_out) *argmax_out = e->h_argmax[0];
+    return FL_OK;
+}
+
+int fl_forward_batch(fl_engine* e, int n_seqs, const int32_t* tokens, const int32_t* pos, int32_t* argmax_out) {
+    if (!e || !tokens || !pos) return set_err(e, FL_ERR_INVALID, "fl_forward_batch: null argument");
+    if (!e->finalized) return set_err(e, FL_ERR_INVALID, "fl_forward_batch: call fl_finalize first");
+    if (n_seqs < 1 || n_seqs > e->c.max_seqs) return set_err(e, FL_ERR_INVALID, "fl_forward_batch: n_seqs %d > max_seqs %d", n_seqs, e->c.max_seqs);
+    CK(e, cudaSetDevice(e->device));
+    for (int i = 0; i < n_seqs; ++i) {
+        if (tokens[i] < 0 || tokens[i] >= e->c.vocab_size || pos[i] < 0 || pos[i] >= e->c.max_seq_len)
+            return set_err(e, FL_ERR_INVALID, "fl_forward_batch: sequence %d: token %d / pos %d out of range", i, tokens[i], pos[i]);
+        e->h_tokens[i] = tokens[i];
+    }
+    CK(e, cudaMemcpyAsync(e->in_tokens, e->h_tokens, sizeof(int) * n_seqs, cudaMemcpyHostToDevice, e->stream));
+    for (int i = 0; i < n_seqs; ++i) {
+        set_state_kernel<<<1, 1, 0, e->stream>>>(e->states + i, e->in_tokens, i, pos[i], 1, 0);
+        e->launches += 1;
+        int rc = run_step(e, i);
+        if (rc) return rc;
+    }
+    if (argmax_out) CK(e, cudaMemcpyAsync(e->h_argmax, e->argmax_dev, sizeof(int) * n_seqs, cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    if (argmax_out) memcpy(argmax_out, e->h_argmax, sizeof(int) * n_seqs);
+    return FL_OK;
+}
+
+int fl_decode_async(fl_engine* e, int seq_slot, int n_steps) {
+    if (!e || !e->finalized) return set_err(e, FL_ERR_INVALID, "fl_decode_async: engine not ready");
+    if (seq_slot < 0 || seq_slot >= e->c.max_seqs || n_steps < 0) return set_err(e, FL_ERR_INVALID, "fl_decode_async: bad argument");
+    CK(e, cudaSetDevice(e->device));
+    for (int i = 0; i < n_steps; ++i) {
+        int rc = run_step(e, seq_slot);
+        if (rc) return rc;
+    }
+    return FL_OK;
+}
+
+int fl_generate_greedy(fl_engine* e, int seq_slot, const int32_t* prompt, int n_prompt, int max_new, int32_t* out_tokens, int* n_out) {
+    if (!e || !prompt || !out_tokens || !n_out) return set_err(e, FL_ERR_INVALID, "fl_generate_greedy: null argument");
+    const fl_config& c = e->c;
+    if (n_prompt < 1 || n_prompt >= c.max_seq_len) return set_err(e, FL_ERR_INVALID, "fl_generate_greedy: prompt length %d not in [1, %d)", n_prompt, c.max_seq_len);
+    if (max_new > c.max_seq_len - n_prompt) max_new = c.max_seq_len - n_prompt;      // transformer.cpp:85-87
+    if (max_new < 0) max_new = 0;
+    int rc = fl_forward(e, seq_slot, prompt, n_prompt, 0, nullptr, nullptr);
+    if (rc) return rc;
+    // transformer.cpp:93-101: one sampled token per forward; max_new further forwards at pos n_prompt ...
+    rc = fl_decode_async(e, seq_slot, max_new);
+    if (rc) return rc;
+    const int total = 1 + max_new;
+    std::vector<int> tmp(total);
+    CK(e, cudaMemcpyAsync(tmp.data(), e->out_tokens + (size_t)seq_slot * e->out_cap, sizeof(int) * total, cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    int n = 0;
+    for (; n < total; ++n) {
+        out_tokens[n] = tmp[n];
+        if (tmp[n] == 0) { ++n; break; }           // generation ends on token id 0 (:93)
+    }
+    *n_out = n;
+    return FL_OK;
+}
+
+void* fl_stream(fl_engine* e) { return e ? (void*)e->stream : nullptr; }
+
+int fl_sync(fl_engine* e) {
+    if (!e) return set_err(e, FL_ERR_INVALID, "fl_sync: null engine");
+    CK(e, cudaSetDevice(e->device));
+    CK(e, cudaStreamSynchronize(e->stream));
+    return FL_OK;
+}
+
+int64_t fl_launch_count(const fl_engine* e) { return e ? e->launches : 0; }
+
+void* fl_device_ptr(fl_engine* e, const char* name, int seq_slot) {
+    if (!e || !name || seq_slot < 0 || seq_slot >= e->c.max_seqs) return nullptr;
+    if (!strcmp(name, "token")) return &e->states[seq_slot].token;          // int32: input token of the next step
+    if (!strcmp(name, "pos")) return &e->states[seq_slot].pos;              // int32
+    if (!strcmp(name, "argmax")) return e->argmax_dev + seq_slot;           // int32: last sampled token
+    if (!strcmp(name, "out_tokens")) return e->out_tokens + (size_t)seq_slot * e->out_cap;
+    if (!strcmp(name, "logits")) return e->logits;                          // fp32[vocab]
+    return nullptr;
+}
+
+int64_t fl_step_bytes(const fl_engine* e, int ctx) {
+    if (!e) return 0;
+    const fl_config& c = e->c;
+    const int64_t kv_dim = (int64_t)c.head_size * c.n_kv_heads;
+    const int64_t P = 2 * (int64_t)c.dim * c.dim + 2 * kv_dim * c.dim + 3 * (int64_t)c.dim * c.hidden_dim;
+    const int64_t params = (int64_t)c.n_layers * P + (int64_t)c.vocab_size * c.dim;
+    const int64_t wbytes = params * es_of(c.quant_type) + params / c.group_size * 4;
+    const int64_t kv = (int64_t)(ctx + 1) * 2 * c.n_layers * kv_dim * 4;
+    return wbytes + kv;
+}
+
+int fl_tap(fl_engine* e, const char* name, float* out, int cap) {
+    if (!e || !name || !out) return set_err(e, FL_ERR_INVALID, "fl_tap: null argument");
+    const fl_config& c = e->c;
+    const int kv_dim = c.head_size * c.n_kv_heads;
+    const float* src = nullptr;
+    int n = 0;
+    if (!strcmp(name, "x1")) { src = e->x1; n = c.dim; }
+    else if (!strcmp(name, "qkv")) { src = e->tap_qkv; n = c.dim + 2 * kv_dim; }
+    else if (!strcmp(name, "attn")) { src = e->attn; n = c.dim; }
+    else if (!strcmp(name, "hd")) { src = e->hd; n = c.hidden_dim; }
+    else if (!strcmp(name, "final")) { src = e->tap_norm; n = c.dim; }
+    else if (!strcmp(name, "logits")) { src = e->logits; n = c.vocab_size; }
+    else return set_err(e, FL_ERR_INVALID, "fl_tap: unknown tap '%s'", name);
+    if (cap < n) return set_err(e, FL_ERR_INVALID, "fl_tap: buffer too small (%d < %d)", cap, n);
+    CK(e, cudaSetDevice(e->device));
+    CK(e, cudaStreamSynchronize(e->stream));
+    CK(e, cudaMemcpy(out, src, sizeof(float) * n, cudaMemcpyDeviceToHost));
+    return n;
+}
+
+// ---- NCCL: weights replicated, request batch sharded; one all-gather of sampled tokens per step ------------
+typedef int (*nccl_allgather_fn)(const void*, void*, size_t, int, void*, cudaStream_t);
+
+int fl_set_comm(fl_engine* e, void* nccl_comm, int rank, int world) {
+    if (!e || world < 1 || rank < 0 || rank >= world) return set_err(e, FL_ERR_INVALID, "fl_set_comm: bad argument");
+    e->rank = rank; e->world = world; e->nccl_comm = nccl_comm;
+    if (world > 1) {
+        if (!nccl_comm) return set_err(e, FL_ERR_INVALID, "fl_set_comm: world > 1 needs a communicator");
+        if (!e->nccl_lib) e->nccl_lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!e->nccl_lib) return set_err(e, FL_ERR_NCCL, "fl_set_comm: cannot dlopen libnccl.so.2: %s", dlerror());
+    }
+    return FL_OK;
+}
+
+int fl_allgather_tokens(fl_engine* e, const int32_t* local, int n_local, int32_t* all) {
+    if (!e || !local || !all || n_local < 1 || n_local > 1024 || e->world > 16) return set_err(e, FL_ERR_INVALID, "fl_allgather_tokens: bad argument");
+    if (e->world == 1) { memcpy(all, local, sizeof(int) * n_local); return FL_OK; }
+    auto fn = (nccl_allgather_fn)dlsym(e->nccl_lib, "ncclAllGather");
+    if (!fn) return set_err(e, FL_ERR_NCCL, "fl_allgather_tokens: ncclAllGather not found");
+    CK(e, cudaSetDevice(e->device));
+    CK(e, cudaMemcpyAsync(e->ag_send, local, sizeof(int) * n_local, cudaMemcpyHostToDevice, e->stream));
+    const int ncclInt32 = 2;
+    int rc = fn(e->ag_send, e->ag_recv, (size_t)n_local, ncclInt32, e->nccl_comm, e->stream);
+    if (rc != 0) return set_err(e, FL_ERR_NCCL, "ncclAllGather failed: %d", rc);
+    CK(e, cudaMemcpyAsync(all, e->ag_recv, sizeof(int) * n_local * e->world, cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    return FL_OK;
+}
+
+// =================================================================================================
+// per-operator entry points
+// =================================================================================================
+
+int fl_op_quantize(int quant_type, int group_size, const float* x, int n, void* q_out, float* scales_out) {
+    if (!x || !q_out || !scales_out || n < group_size || n % group_size) return set_err(nullptr, FL_ERR_INVALID, "fl_op_quantize: bad argument");
+    if (int rc = need_device()) return rc;
+    const int es = es_of(quant_type);
+    DevBuf dx, dq, ds;
+    if (dx.alloc((size_t)n * 4) || dq.alloc((size_t)n * es) || ds.alloc((size_t)n / group_size * 4)) return set_err(nullptr, FL_ERR_OOM, "fl_op_quantize: cudaMalloc");
+    CKO(cudaMemcpy(dx.p, x, (size_t)n * 4, cudaMemcpyHostToDevice));
+    const int nkb = ceil_div(n, kKBlockElems);
+    const size_t smem = (size_t)nkb * kKBlockElems * es + (size_t)n / group_size * 4 + 64;
+    int rc = dispatch_q(quant_type, group_size, [&](auto QT, auto GS) -> int {
+        auto kern = op_quantize_kernel<decltype(QT)::value, decltype(GS)::value>;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kern<<<1, kThreads, smem>>>(dx.as<float>(), n, dq.p, ds.as<float>());
+        return FL_OK;
+    });
+    if (rc) return set_err(nullptr, rc, "fl_op_quantize: unsupported quantisation");
+    CKO(cudaGetLastError());
+    CKO(cudaMemcpy(q_out, dq.p, (size_t)n * es, cudaMemcpyDeviceToHost));
+    CKO(cudaMemcpy(scales_out, ds.p, (size_t)n / group_size * 4, cudaMemcpyDeviceToHost));
+    return FL_OK;
+}
+
+int fl_op_matmul_q(int quant_type, int group_size, const void* w, const float* w_scales, int m, int n,
+                   const void* x, const float* x_scales, int rows_x, float* out) {
+    if (!w || !w_scales || !x || !x_scales || !out || m < 1 || n < group_size || n % group_size || rows_x < 1)
+        return set_err(nullptr, FL_ERR_INVALID, "fl_op_matmul_q: bad argument");
+    if (int rc = need_device()) return rc;
+    const int es = es_of(quant_type);
+    const int G = n / group_size;
+    const int n_tiles = ceil_div(m, 4), nkb = ceil_div(n, kKBlockElems);
+    const size_t pbytes = (size_t)n_tiles * nkb * unit_bytes(quant_type, group_size);
+    DevBuf dw, dws, dp, dx, dxs, dout;
+    if (dw.alloc((size_t)m * n * es) || dws.alloc((size_t)m * G * 4) || dp.alloc(pbytes) || dx.alloc((size_t)rows_x * n * es) ||
+        dxs.alloc((size_t)rows_x * G * 4) || dout.alloc((size_t)rows_x * m * 4))
+        return set_err(nullptr, FL_ERR_OOM, "fl_op_matmul_q: cudaMalloc");
+    CKO(cudaMemcpy(dw.p, w, (size_t)m * n * es, cudaMemcpyHostToDevice));
+    CKO(cudaMemcpy(dws.p, w_scales, (size_t)m * G * 4, cudaMemcpyHostToDevice));
+    CKO(cudaMemcpy(dx.p, x, (size_t)rows_x * n * es, cudaMemcpyHostToDevice));
+    CKO(cudaMemcpy(dxs.p, x_scales, (size_t)rows_x * G * 4, cudaMemcpyHostToDevice));
+    int rc = dispatch_q(quant_type, group_size, [&](auto QT, auto GS) -> int {
+        pack_weights_kernel<decltype(QT)::value, decltype(GS)::value><<<512, 256>>>(dw.as<uint8_t>(), dws.as<float>(), dp.as<uint8_t>(), m, n, n_tiles, nkb, 1, 0);
+        return FL_OK;
+    });
+    if (rc) return set_err(nullptr, rc, "fl_op_matmul_q: unsupported quantisation");
+    CKO(cudaGetLastError());
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    for (int i = 0; i < rows_x; ++i) {
+        GemvArgs a{};
+        a.w = dp.as<uint8_t>(); a.M = m; a.K = n; a.n_tasks = n_tiles; a.nkb = nkb;
+        a.in_q = dx.as<uint8_t>() + (size_t)i * n * es; a.in_s = dxs.as<float>() + (size_t)i * G;
+        a.out = dout.as<float>() + (size_t)i * m;
+        int grid = ceil_div(n_tiles, kWarps);
+        if (grid > sms * 2) grid = sms * 2;
+        rc = launch_gemv<PRO_LOADQ, EPI_STORE>(nullptr, quant_type, group_size, a, grid, 0);
+        if (rc) return rc;
+    }
+    CKO(cudaDeviceSynchronize());
+    CKO(cudaMemcpy(out, dout.p, (size_t)rows_x * m * 4, cudaMemcpyDeviceToHost));
+    return FL_OK;
+}
+
+int fl_op_rmsnorm(const float* x, const float* w, int n, float* out) {
+    if (!x || !w || !out || n < 32 || n % 8) return set_err(nullptr, FL_ERR_INVALID, "fl_op_rmsnorm: n must be a multiple of 8, >= 32");
+    if (int rc = need_device()) return rc;
+    DevBuf dx, dw, dout;
+    if (dx.alloc((size_t)n * 4) || dw.alloc((size_t)n * 4) || dout.alloc((size_t)n * 4)) return set_err(nullptr, FL_ERR_OOM, "fl_op_rmsnorm: cudaMalloc");
+    CKO(cudaMemcpy(dx.p, x, (size_t)n * 4, cudaMemcpyHostToDevice));
+    CKO(cudaMemcpy(dw.p, w, (size_t)n * 4, cudaMemcpyHostToDevice));
+    cudaFuncSetAttribute(op_rmsnorm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, n * 4);
+    op_rmsnorm_kernel<<<1, kThreads, (size_t)n * 4>>>(dx.as<float>(), dw.as<float>(), n, dout.as<float>());
+    CKO(cudaGetLastError());
+    CKO(cudaMemcpy(out, dout.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    return FL_OK;
+}
+
+int fl_op_rope(const float* x, int n_dims, int pos, float* out) {
+    if (!x || !out || n_dims < 2 || n_dims > 1024 || n_dims % 2 || pos < 0) return set_err(nullptr, FL_ERR_INVALID, "fl_op_rope: bad argument");
+    if (int rc = need_device()) return rc;
+    std::vector<float> tab((size_t)n_dims);
+    {
+        const float theta_scale = powf(10000.0f, -2.0f / (float)n_dims);
+        float theta = (float)pos;
+        for (int i = 0; i < n_dims; i += 2) { float s, c; sincosf(theta, &s, &c); tab[i] = c; tab[i + 1] = s; theta *= theta_scale; }
+    }
+    DevBuf dx, dt, dout;
+    if (dx.alloc((size_t)n_dims * 4) || dt.alloc((size_t)n_dims * 4) || dout.alloc((size_t)n_dims * 4)) return set_err(nullptr, FL_ERR_OOM, "fl_op_rope: cudaMalloc");
+    CKO(cudaMemcpy(dx.p, x, (size_t)n_dims * 4, cudaMemcpyHostToDevice));
+    CKO(cudaMemcpy(dt.p, tab.data(), (size_t)n_dims * 4, cudaMemcpyHostToDevice));
+    op_rope_kernel<<<1, 512>>>(dx.as<float>(), dt.as<float>(), n_dims, dout.as<float>());
+    CKO(cudaGetLastError());
+    CKO(cudaMemcpy(out, dout.p, (size_t)n_dims * 4, cudaMemcpyDeviceToHost));
+    return FL_OK;
+}
+
+static int unary_op(const float* x, int n, float* out, int which, const float* b) {
+    if (!x || !out || n < 1) return set_err(nullptr, FL_ERR_INVALID, "fl_op: bad argument");
+    if (int rc = need_device()) return rc;
+    DevBuf dx, db, dout;
+    if (dx.alloc((size_t)n * 4) || dout.alloc((size_t)n * 4) || (b && db.alloc((size_t)n * 4))) return set_err(nullptr, FL_ERR_OOM, "fl_op: cudaMalloc");
+    CKO(cudaMemcpy(dx.p, x, (size_t)n * 4, cudaMemcpyHostToDevice));
+    if (b) CKO(cudaMemcpy(db.p, b, (size_t)n * 4, cudaMemcpyHostToDevice));
+    if (which == 0) op_softmax_kernel<<<1, kThreads>>>(dx.as<float>(), n, dout.as<float>());
+    else if (which == 1) op_swiglu_kernel<<<296, 256>>>(dx.as<float>(), db.as<float>(), n, dout.as<float>());
+    else op_expf_kernel<<<296, 256>>>(dx.as<float>(), n, dout.as<float>());
+    CKO(cudaGetLastError());
+    CKO(cudaMemcpy(out, dout.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    return FL_OK;
+}
+
+int fl_op_softmax(const float* x, int n, float* out) { return unary_op(x, n, out, 0, nullptr); }
+int fl_op_swiglu(const float* a, const float* b, int n, float* out) {
+    if (!b) return set_err(nullptr, FL_ERR_INVALID, "fl_op_swiglu: null argument");
+    return unary_op(a, n, out, 1, b);
+}
+int fl_op_expf(const float* x, int n, float* out) { return unary_op(x, n, out, 2, nullptr); }
+
+int fl_op_attn_decode(int n_heads, int n_kv_heads, int head_size, int pos, const float* qkv,
+                      const float* k_cache, const float* v_cache, float* out, float* k_new, float* v_new) {
+    if (!qkv || !out || n_heads < 1 || n_kv_heads < 1 || n_heads % n_kv_heads || pos < 0 || (pos > 0 && (!k_cache || !v_cache)))
+        return set_err(nullptr, FL_ERR_INVALID, "fl_op_attn_decode: bad argument");
+    if (head_size != 64 && head_size != 128) return set_err(nullptr, FL_ERR_UNSUPPORTED, "fl_op_attn_decode: head_size must be 64 or 128");
+    if (int rc = need_device()) return rc;
+    const int hs = head_size, dim = n_heads * hs, kv_dim = n_kv_heads * hs, hgs = n_heads / n_kv_heads;
+    const int max_seq = pos + 1;
+    std::vector<float> tab;
+    build_rope_table(tab, max_seq + hgs, hs);
+    DevBuf dqkv, dk, dv, dknat, dtab, dpos, dbs, dout;
+    const size_t cache = (size_t)n_kv_heads * max_seq * hs;
+    if (dqkv.alloc((size_t)(dim + 2 * kv_dim) * 4) || dk.alloc(cache * 4) || dv.alloc(cache * 4) || dknat.alloc(cache * 4) ||
+        dtab.alloc(tab.size() * 4) || dpos.alloc(4) || dbs.alloc(4) || dout.alloc((size_t)dim * 4))
+        return set_err(nullptr, FL_ERR_OOM, "fl_op_attn_decode: cudaMalloc");
+    CKO(cudaMemset(dk.p, 0, cache * 4));
+    CKO(cudaMemset(dv.p, 0, cache * 4));
+    CKO(cudaMemcpy(dqkv.p, qkv, (size_t)(dim + 2 * kv_dim) * 4, cudaMemcpyHostToDevice));
+    CKO(cudaMemcpy(dtab.p, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
+    CKO(cudaMemcpy(dpos.p, &pos, 4, cudaMemcpyHostToDevice));
+    const int one = 1;
+    CKO(cudaMemcpy(dbs.p, &one, 4, cudaMemcpyHostToDevice));
+    for (int h = 0; h < n_kv_heads && pos > 0; ++h) {   // host rows are [kv_head][pos][hs]; device rows [kv_head][max_seq][hs]
+        CKO(cudaMemcpy(dknat.as<float>() + (size_t)h * max_seq * hs, k_cache + (size_t)h * pos * hs, (size_t)pos * hs * 4, cudaMemcpyHostToDevice));
+        CKO(cudaMemcpy(dv.as<float>() + (size_t)h * max_seq * hs, v_cache + (size_t)h * pos * hs, (size_t)pos * hs * 4, cudaMemcpyHostToDevice));
+    }
+    permute_k_rows_kernel<<<256, 256>>>(dknat.as<float>(), dk.as<float>(), n_kv_heads * max_seq, hs);
+    CKO(cudaGetLastError());
+    AttnArgs a{};
+    a.qkv = dqkv.as<float>(); a.k_cache = dk.as<float>(); a.v_cache = dv.as<float>(); a.rope = dtab.as<float>();
+    a.pos_ptr = dpos.as<int>(); a.bs_ptr = dbs.as<int>(); a.out = dout.as<float>(); a.tap_qkv = nullptr;
+    a.n_heads = n_heads; a.n_kv_heads = n_kv_heads; a.max_seq = max_seq; a.attn_scale = 1.0f / sqrtf((float)hs);
+    int rc = launch_attn(nullptr, hs, a, max_seq, 0);
+    if (rc) return rc;
+    CKO(cudaDeviceSynchronize());
+    CKO(cudaMemcpy(out, dout.p, (size_t)dim * 4, cudaMemcpyDeviceToHost));
+    if (k_new || v_new) {
+        std::vector<float> row(hs);
+        for (int h = 0; h < n_kv_heads; ++h) {
+            if (k_new) {
+                CKO(cudaMemcpy(row.data(), dk.as<float>() + ((size_t)h * max_seq + pos) * hs, (size_t)hs * 4, cudaMemcpyDeviceToHost));
+                for (int e2 = 0; e2 < hs; ++e2) k_new[(size_t)h * hs + e2] = row[(e2 & 7) * (hs / 8) + (e2 >> 3)];
+            }
+            if (v_new) CKO(cudaMemcpy(v_new + (size_t)h * hs, dv.as<float>() + ((size_t)h * max_seq + pos) * hs, (size_t)hs * 4, cudaMemcpyDeviceToHost));
+        }
+    }
+    return FL_OK;
+}
+
+int fl_op_argmax(const float* logits, int n, int32_t* out) {
+    if (!logits || !out || n < 1) return set_err(nullptr, FL_ERR_INVALID, "fl_op_argmax: bad argument");
+    if (int rc = need_device()) return rc;
+    DevBuf dl, dr;
+    if (dl.alloc((size_t)n * 4) || dr.alloc(4)) return set_err(nullptr, FL_ERR_OOM, "fl_op_argmax: cudaMalloc");
+    CKO(cudaMemcpy(dl.p, logits, (size_t)n * 4, cudaMemcpyHostToDevice));
+    argmax_kernel<<<1, 1024>>>(dl.as<float>(), n, nullptr, nullptr, 0, dr.as<int>(), 0);
+    CKO(cudaGetLastError());
+    CKO(cudaMemcpy(out, dr.p, 4, cudaMemcpyDeviceToHost));
+    return FL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,166 @@
+"""GPU parity, model level: fl_forward / fl_generate_greedy (through the C-ABI) against the CPU oracle's forward()
+on the same seeded weights and token ids.  Logits must be BIT-identical (so greedy token ids are identical too),
+for INT8 and INT16, group 64 and 32, MHA and GQA.  Golden logits generated from the real reference
+(tests/golden/make_golden.py) are checked as well, so the chain GPU == port == reference is closed on the GPU box
+where /root/reference does not exist."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from oracle_libs import port, ptr, bits, PortConfig, Q_INT8, Q_INT16
+from fixtures import (ModelSpec, TINY, TINY64, gen_weights, quantize_model, prompt_tokens)
+
+pytestmark = pytest.mark.gpu
+
+GQA = ModelSpec(dim=512, hidden_dim=704, n_layers=2, n_heads=8, n_kv_heads=2, vocab_size=1000)
+
+
+def make_port_model(spec, qm, qt, gs, max_seq=1024):
+    P = port()
+    pc = PortConfig(spec.dim, spec.hidden_dim, spec.n_layers, spec.n_heads, spec.n_kv_heads, spec.head_size,
+                    spec.vocab_size, max_seq, qt, gs)
+    pm = P.port_model_create(C.byref(pc))
+    for (k, l), (q, s) in qm.items():
+        rows = q.shape[0] if q.ndim == 2 else 1
+        assert P.port_model_set_tensor(pm, k, l, ptr(q), ptr(s) if s is not None else None, rows, q.shape[-1]) == 0
+    return pm
+
+
+def make_engine(fl, spec, qm, qt, gs, max_seq=1024, **kw):
+    e = fl.Engine(spec.dim, spec.hidden_dim, spec.n_layers, spec.n_heads, spec.n_kv_heads, spec.vocab_size,
+                  max_seq_len=max_seq, quant_type=qt, group_size=gs, **kw)
+    e.upload_model(qm)
+    return e
+
+
+CASES = [
+    ("tiny-int8", TINY, Q_INT8, 64, True),
+    ("tiny64-int8", TINY64, Q_INT8, 64, True),
+    ("tiny-int16", TINY, Q_INT16, 64, False),
+    ("tiny-int8-g32", TINY, Q_INT8, 32, False),
+    ("gqa-int8", GQA, Q_INT8, 64, True),
+]
+
+
+@pytest.mark.parametrize("name,spec,qt,gs,qemb", CASES, ids=[c[0] for c in CASES])
+def test_forward_logits_bit_exact(fl, name, spec, qt, gs, qemb):
+    w = gen_weights(spec, seed=1)
+    qm = quantize_model(spec, w, qt, gs, quantize_embedding=qemb)
+    pm = make_port_model(spec, qm, qt, gs)
+    eng = make_engine(fl, spec, qm, qt, gs)
+    P = port()
+    toks = prompt_tokens(spec, 6, seed=3)
+    want = np.empty(spec.vocab_size, np.float32)
+    P.port_forward(pm, ptr(toks), toks.size, 0, ptr(want))
+    got = eng.forward(toks, 0)
+    for tap in ("qkv", "attn", "hd", "x1", "final"):       # last layer taps: localise a mismatch
+        n = C.c_int(0)
+        pt = P.port_tap(pm, tap.encode(), spec.n_layers - 1, C.byref(n))
+        ref_tap = np.ctypeslib.as_array(pt, (n.value,)).copy()
+        gpu_tap = eng.tap(tap)
+        assert np.array_equal(bits(gpu_tap), bits(ref_tap)), (name, tap, np.abs(gpu_tap - ref_tap).max())
+    assert np.array_equal(bits(got), bits(want)), (name, np.abs(got - want).max())
+    pos = toks.size
+    for step in range(24):
+        t = np.array([int(np.argmax(want))], np.int32)
+        P.port_forward(pm, ptr(t), 1, pos, ptr(want))
+        got, am = eng.forward(t, pos, want_argmax=True)
+        assert np.array_equal(bits(got), bits(want)), (name, step, np.abs(got - want).max())
+        assert am == P.port_argmax(ptr(want), spec.vocab_size)
+        pos += 1
+    P.port_model_free(pm)
+    eng.close()
+
+
+def test_generate_greedy_matches_oracle_and_graph_equals_direct(fl):
+    spec, qt, gs = TINY, Q_INT8, 64
+    w = gen_weights(spec, seed=2)
+    qm = quantize_model(spec, w, qt, gs)
+    pm = make_port_model(spec, qm, qt, gs)
+    P = port()
+    prompt = prompt_tokens(spec, 9, seed=5)
+    n_new = 40
+    logits = np.empty(spec.vocab_size, np.float32)
+    P.port_forward(pm, ptr(prompt), prompt.size, 0, ptr(logits))
+    want = [P.port_argmax(ptr(logits), spec.vocab_size)]
+    pos = prompt.size
+    for _ in range(n_new):                                   # transformer.cpp:93-101
+        if want[-1] == 0:
+            break
+        t = np.array([want[-1]], np.int32)
+        P.port_forward(pm, ptr(t), 1, pos, ptr(logits))
+        want.append(P.port_argmax(ptr(logits), spec.vocab_size))
+        pos += 1
+    outs = []
+    for flags in (0, fl.FLAG_NO_GRAPH):
+        eng = make_engine(fl, spec, qm, qt, gs, flags=flags)
+        before = eng.launch_count()
+        outs.append(eng.generate_greedy(prompt, n_new))
+        assert eng.launch_count() > before
+        eng.close()
+    assert outs[0].tolist() == want
+    assert outs[1].tolist() == want
+    P.port_model_free(pm)
+
+
+def test_kv_slots_are_independent_and_batch_matches_single(fl):
+    spec, qt, gs = TINY, Q_INT8, 64
+    w = gen_weights(spec, seed=4)
+    qm = quantize_model(spec, w, qt, gs)
+    eng = make_engine(fl, spec, qm, qt, gs, max_seqs=3)
+    prompts = [prompt_tokens(spec, n, seed=s) for n, s in ((4, 1), (7, 2), (5, 3))]
+    single = []
+    for i, p in enumerate(prompts):
+        single.append(eng.generate_greedy(p, 6, slot=0).tolist())
+    # same sequences interleaved across three slots via fl_forward_batch
+    firsts = [eng.forward(p, 0, slot=i, want_logits=False, want_argmax=True) for i, p in enumerate(prompts)]
+    toks = np.array(firsts, np.int32)
+    pos = np.array([p.size for p in prompts], np.int32)
+    outs = [[int(t)] for t in toks]
+    for _ in range(6):
+        toks = eng.forward_batch(toks, pos)
+        pos += 1
+        for i, t in enumerate(toks):
+            outs[i].append(int(t))
+    for i in range(3):
+        n = len(single[i])
+        assert outs[i][:n] == single[i]
+    eng.close()
+
+
+def test_error_behaviour(fl):
+    spec = TINY
+    with pytest.raises(fl.FlError):
+        fl.Engine(spec.dim, spec.hidden_dim, spec.n_layers, 3, 3, spec.vocab_size)          # head_size*n_heads != dim
+    eng = fl.Engine(spec.dim, spec.hidden_dim, spec.n_layers, spec.n_heads, spec.n_kv_heads, spec.vocab_size)
+    with pytest.raises(fl.FlError):
+        eng.finalize()                                                                      # nothing uploaded
+    with pytest.raises(fl.FlError):
+        eng.upload(fl.T_WQ, 0, np.zeros((8, 8), np.int8), np.zeros((8, 1), np.float32))     # wrong shape
+    with pytest.raises(fl.FlError):
+        eng.forward(np.array([1], np.int32), 0)                                             # not finalized
+    eng.close()
+
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "tiny_model_logits.npz")
+
+
+@pytest.mark.skipif(not os.path.exists(GOLDEN), reason="golden vectors not generated")
+def test_forward_matches_reference_golden_logits(fl):
+    """Logits produced by the REAL reference (oracle/_ref/libref.so, llama2.c checkpoint path) for the seeded TINY model."""
+    g = np.load(GOLDEN)
+    spec = TINY
+    w = gen_weights(spec, seed=int(g["seed"]))
+    qm = quantize_model(spec, w, Q_INT8, 64)
+    eng = make_engine(fl, spec, qm, Q_INT8, 64)
+    toks = g["prompt"].astype(np.int32)
+    got = eng.forward(toks, 0)
+    assert np.array_equal(bits(got), bits(g["prefill_logits"]))
+    pos = toks.size
+    for i, t in enumerate(g["decode_tokens"]):
+        got = eng.forward(np.array([t], np.int32), pos)
+        assert np.array_equal(bits(got), bits(g["decode_logits"][i])), i
+        pos += 1
+    eng.close()
