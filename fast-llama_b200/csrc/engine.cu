@@ -6,6 +6,7 @@
 // caller asks for logits.  There is no CPU path: every entry point needs a CUDA device.
 #include "../../include/fastllama_b200.h"
 #include "kernels.cuh"
+#include "megakernel.cuh"
 
 #include <dlfcn.h>
 #include <math.h>
@@ -75,6 +76,16 @@ struct fl_engine {
     float* h_logits = nullptr;          // pinned
     int* h_argmax = nullptr;            // pinned
     std::vector<cudaGraphExec_t> graphs;
+    // megakernel state
+    bool use_mega = false;
+    MegaLayer* mega_layers = nullptr;
+    float* att_scratch = nullptr;
+    unsigned long long* bar_ctr = nullptr;
+    unsigned long long* head_ctr = nullptr;
+    float* am_val = nullptr;
+    int* am_idx = nullptr;
+    MegaParams mega{};
+    size_t mega_smem = 0;
     bool finalized = false;
     int64_t launches = 0;
     int kernels_per_step = 0;
@@ -268,7 +279,110 @@ int enqueue_step(fl_engine* e, int slot, cudaStream_t st, int* n_kernels) {
     return FL_OK;
 }
 
+template <typename F>
+int dispatch_mega(int qt, int gs, int hs, F&& f) {
+    if (qt == FL_Q_INT8 && gs == 64 && hs == 128) return f(decode_megakernel<Q_INT8, 64, 128>);
+    if (qt == FL_Q_INT8 && gs == 64 && hs == 64) return f(decode_megakernel<Q_INT8, 64, 64>);
+    if (qt == FL_Q_INT8 && gs == 32 && hs == 128) return f(decode_megakernel<Q_INT8, 32, 128>);
+    if (qt == FL_Q_INT8 && gs == 32 && hs == 64) return f(decode_megakernel<Q_INT8, 32, 64>);
+    if (qt == FL_Q_INT16 && gs == 64 && hs == 128) return f(decode_megakernel<Q_INT16, 64, 128>);
+    if (qt == FL_Q_INT16 && gs == 64 && hs == 64) return f(decode_megakernel<Q_INT16, 64, 64>);
+    return FL_ERR_UNSUPPORTED;
+}
+
+// one-time set-up of the persistent decode kernel: layer table, counters, shared-memory carve-up
+int setup_mega(fl_engine* e) {
+    const fl_config& c = e->c;
+    const int L = c.n_layers, qt = c.quant_type, gs = c.group_size, es = es_of(qt), gpl = 64 / gs;
+    std::vector<MegaLayer> tab(L);
+    for (int l = 0; l < L; ++l) {
+        tab[l].qkv = e->qkv[l].d; tab[l].wo = e->wo[l].d; tab[l].w13 = e->w13[l].d; tab[l].w2 = e->w2[l].d;
+        tab[l].att_norm = e->att_norm + (size_t)l * c.dim; tab[l].ffn_norm = e->ffn_norm + (size_t)l * c.dim;
+    }
+    CK(e, cudaMalloc(&e->mega_layers, sizeof(MegaLayer) * L));
+    CK(e, cudaMemcpy(e->mega_layers, tab.data(), sizeof(MegaLayer) * L, cudaMemcpyHostToDevice));
+    CK(e, cudaMalloc(&e->att_scratch, (size_t)c.n_heads * c.max_seq_len * 4));
+    CK(e, cudaMalloc(&e->bar_ctr, 2 * sizeof(unsigned long long)));
+    CK(e, cudaMemset(e->bar_ctr, 0, 2 * sizeof(unsigned long long)));
+    CK(e, cudaMalloc(&e->head_ctr, 2 * (size_t)c.n_heads * sizeof(unsigned long long)));
+    CK(e, cudaMemset(e->head_ctr, 0, 2 * (size_t)c.n_heads * sizeof(unsigned long long)));
+    CK(e, cudaMalloc(&e->am_val, sizeof(float) * e->n_sms));
+    CK(e, cudaMalloc(&e->am_idx, sizeof(int) * e->n_sms));
+    MegaParams& p = e->mega;
+    p.layers = e->mega_layers; p.cls = e->cls.d; p.out_norm = e->out_norm; p.emb = e->emb;
+    p.x1 = e->x1; p.qkv = e->qkv_buf; p.attn = e->attn; p.hd = e->hd; p.logits = e->logits; p.att_scratch = e->att_scratch;
+    p.rope = e->rope; p.out_cap = e->out_cap;
+    p.bar_ctr = e->bar_ctr; p.head_ctr = e->head_ctr; p.am_val = e->am_val; p.am_idx = e->am_idx; p.tap_norm = e->tap_norm;
+    p.dim = c.dim; p.hidden = c.hidden_dim; p.n_layers = L; p.n_heads = c.n_heads; p.n_kv_heads = c.n_kv_heads;
+    p.vocab = c.vocab_size; p.max_seq = c.max_seq_len; p.qkv_rows = c.dim + 2 * c.head_size * c.n_kv_heads;
+    p.attn_scale = 1.0f / sqrtf((float)c.head_size);
+    int cph = 4;
+    while (cph > 1 && (c.n_heads * cph > e->n_sms || c.head_size / cph < 16)) cph /= 2;
+    if (c.n_heads > e->n_sms) return set_err(e, FL_ERR_UNSUPPORTED, "megakernel: n_heads %d > SM count %d", c.n_heads, e->n_sms);
+    p.cph = cph;
+    const int dw = c.head_size / cph;
+    p.v_chunk_rows = 2048 / dw;
+    // shared memory carve-up
+    const int nkb_max = ceil_div(c.dim > c.hidden_dim ? c.dim : c.hidden_dim, kKBlockElems);
+    auto al = [](size_t v, size_t a) { return (v + a - 1) / a * a; };
+    size_t off = 0;
+    p.off_misc = (int)off; off += 2048;
+    p.off_chain = (int)off; off += (size_t)kConsumerWarps * 2 * 32 * 2 * gpl * 4;
+    p.off_att = (int)off; off += al((size_t)c.max_seq_len * 4, 128);
+    p.off_xs = (int)off; off += al((size_t)nkb_max * 8 * gpl * 4, 128);
+    const size_t xq_bytes = (size_t)nkb_max * kKBlockElems * es, xf_bytes = (size_t)c.dim * 4;
+    size_t scratch = xq_bytes + xf_bytes;
+    const size_t vneed = 3 * (size_t)p.v_chunk_rows * dw * 4;
+    if (scratch < vneed) scratch = vneed;
+    p.off_xq = (int)off; p.off_vstage = (int)off; p.off_xf = (int)(off + xq_bytes); off += al(scratch, 128);
+    int max_smem = 0;
+    CK(e, cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, e->device));
+    const size_t slot_bytes = (size_t)(qt == FL_Q_INT8 ? 4 : 2) * unit_bytes(qt, gs);
+    int n_slots = (int)(((size_t)max_smem - off - 1024) / (slot_bytes + 16));
+    if (n_slots > 32) n_slots = 32;
+    if (n_slots < 4) return set_err(e, FL_ERR_UNSUPPORTED, "megakernel: not enough shared memory for the weight ring (%d slots)", n_slots);
+    p.n_slots = n_slots;
+    p.off_bars = (int)off; off += al((size_t)n_slots * 16, 128);
+    p.off_ring = (int)off; off += (size_t)n_slots * slot_bytes;
+    e->mega_smem = off;
+    int rc = dispatch_mega(qt, gs, c.head_size, [&](auto kern) -> int {
+        cudaError_t s = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->mega_smem);
+        if (s != cudaSuccess) return set_err(e, FL_ERR_CUDA, "cudaFuncSetAttribute(megakernel, %zu): %s", e->mega_smem, cudaGetErrorString(s));
+        int nb = 0;
+        s = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kMegaThreads, e->mega_smem);
+        if (s != cudaSuccess || nb < 1) return set_err(e, FL_ERR_CUDA, "megakernel does not fit an SM (smem %zu)", e->mega_smem);
+        return FL_OK;
+    });
+    if (rc == FL_ERR_UNSUPPORTED) return set_err(e, rc, "megakernel: unsupported quant/group/head combination");
+    return rc;
+}
+
+int launch_mega(fl_engine* e, int slot, int n_steps) {
+    const fl_config& c = e->c;
+    MegaParams p = e->mega;
+    const size_t cache_per_slot = (size_t)c.n_layers * c.n_kv_heads * c.max_seq_len * c.head_size;
+    p.k_cache = e->k_cache + slot * cache_per_slot;
+    p.v_cache = e->v_cache + slot * cache_per_slot;
+    p.st = e->states + slot;
+    p.out_tokens = e->out_tokens + (size_t)slot * e->out_cap;
+    p.argmax_out = e->argmax_dev + slot;
+    p.n_steps = n_steps;
+    return dispatch_mega(c.quant_type, c.group_size, c.head_size, [&](auto kern) -> int {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(e->n_sms); cfg.blockDim = dim3(kMegaThreads); cfg.dynamicSmemBytes = e->mega_smem; cfg.stream = e->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeCooperative;        // every CTA resident: the grid barriers cannot deadlock
+        attr[0].val.cooperative = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        cudaError_t s = cudaLaunchKernelEx(&cfg, kern, p);
+        if (s != cudaSuccess) return set_err(e, FL_ERR_CUDA, "megakernel launch: %s", cudaGetErrorString(s));
+        e->launches += 1;
+        return FL_OK;
+    });
+}
+
 int run_step(fl_engine* e, int slot) {
+    if (e->use_mega) return launch_mega(e, slot, 1);
     if (e->c.flags & FL_FLAG_NO_GRAPH) {
         int nk = 0;
         int rc = enqueue_step(e, slot, e->stream, &nk);
@@ -413,6 +527,7 @@ void fl_destroy(fl_engine* e) {
     fr(e->x1); fr(e->qkv_buf); fr(e->attn); fr(e->hd); fr(e->logits); fr(e->tap_qkv); fr(e->tap_norm);
     fr(e->k_cache); fr(e->v_cache); fr(e->rope); fr(e->states); fr(e->out_tokens); fr(e->in_tokens); fr(e->argmax_dev);
     fr(e->ag_send); fr(e->ag_recv);
+    fr(e->mega_layers); fr(e->att_scratch); fr(e->bar_ctr); fr(e->head_ctr); fr(e->am_val); fr(e->am_idx);
     if (e->h_tokens) cudaFreeHost(e->h_tokens);
     if (e->h_logits) cudaFreeHost(e->h_logits);
     if (e->h_argmax) cudaFreeHost(e->h_argmax);
@@ -502,6 +617,11 @@ int fl_finalize(fl_engine* e) {
     CK(e, cudaMalloc(&e->rope, tab.size() * 4));
     CK(e, cudaMemcpy(e->rope, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
     if (e->staging) { cudaFree(e->staging); e->staging = nullptr; }
+    if (!(c.flags & FL_FLAG_NO_MEGAKERNEL)) {
+        int rc = setup_mega(e);
+        if (rc) return rc;
+        e->use_mega = true;
+    }
     e->finalized = true;
     return FL_OK;
 }
@@ -562,6 +682,7 @@ int fl_decode_async(fl_engine* e, int seq_slot, int n_steps) {
     if (!e || !e->finalized) return set_err(e, FL_ERR_INVALID, "fl_decode_async: engine not ready");
     if (seq_slot < 0 || seq_slot >= e->c.max_seqs || n_steps < 0) return set_err(e, FL_ERR_INVALID, "fl_decode_async: bad argument");
     CK(e, cudaSetDevice(e->device));
+    if (e->use_mega) return n_steps > 0 ? launch_mega(e, seq_slot, n_steps) : FL_OK;   // all steps inside one persistent launch
     for (int i = 0; i < n_steps; ++i) {
         int rc = run_step(e, seq_slot);
         if (rc) return rc;

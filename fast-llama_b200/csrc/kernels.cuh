@@ -233,12 +233,58 @@ struct UnitRegs {
     float s[Traits<QT, GS>::GPL];
 };
 
+// One unit = 4 rows x 512 columns: integer dots of the lane's group(s), then the reference's FP32 chain
+//     o[j] += s * dot  ==  fma(scales1*scales2, (float)dot, o[j]),  groups ascending   (quant_operators.cpp:274-275)
+// The (s, f) pairs of a row's 8 lanes are transposed through a per-warp shared-memory slot so that every lane of the
+// row walks them in group order (redundantly: same instruction stream, no shuffles, no divergence).
+// Padded groups (K % 512 != 0) carry zero weights/scales/activations: fma(0, 0, acc) == acc exactly (acc is never -0).
+template <int QT, int GS>
+__device__ __forceinline__ float unit_chain(const uint4 (&w)[Traits<QT, GS>::NJ], const float (&ws)[Traits<QT, GS>::GPL],
+                                            const uint4* __restrict__ xk, const float* __restrict__ xsk,
+                                            float* __restrict__ cs, int lane, float acc) {
+    using T = Traits<QT, GS>;
+    const int l = lane & 7, r = lane >> 3;
+    // independent partial dots per 16-byte chunk (integer adds are exact in any order), then one add tree per group
+    int dj[T::NJ];
+#pragma unroll
+    for (int j = 0; j < T::NJ; ++j) dj[j] = dot16<QT>(w[j], xk[j * 8 + l], 0);
+    int d[T::GPL];
+#pragma unroll
+    for (int gg = 0; gg < T::GPL; ++gg) d[gg] = 0;
+#pragma unroll
+    for (int j = 0; j < T::NJ; ++j) d[(j * 16) / (GS * T::ES)] += dj[j];
+    if (T::GPL == 1) {
+        reinterpret_cast<float2*>(cs)[lane] = make_float2(__fmul_rn(ws[0], xsk[l]), __int2float_rn(d[0]));
+        __syncwarp();
+        const float4* row = reinterpret_cast<const float4*>(cs) + r * 4;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float4 p = row[i];
+            acc = __fmaf_rn(p.x, p.y, acc);
+            acc = __fmaf_rn(p.z, p.w, acc);
+        }
+    } else {
+        reinterpret_cast<float4*>(cs)[lane] = make_float4(__fmul_rn(ws[0], xsk[l * 2]), __int2float_rn(d[0]),
+                                                          __fmul_rn(ws[T::GPL - 1], xsk[l * 2 + 1]), __int2float_rn(d[T::GPL - 1]));
+        __syncwarp();
+        const float4* row = reinterpret_cast<const float4*>(cs) + r * 8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float4 p = row[i];
+            acc = __fmaf_rn(p.x, p.y, acc);
+            acc = __fmaf_rn(p.z, p.w, acc);
+        }
+    }
+    return acc;
+}
+
 template <int QT, int GS, int PRO, int EPI>
 __global__ void __launch_bounds__(kThreads) gemv_kernel(const GemvArgs a) {
     using T = Traits<QT, GS>;
     constexpr int TT = (EPI == EPI_SWIGLU) ? 2 : 1;        // row tiles per task
     constexpr int DEPTH = (QT == Q_INT8) ? 4 : 2;          // units in flight per warp
     extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ __align__(16) float chain_slots[kWarps][2][32 * 2 * T::GPL];
     const int K = a.K, G = K / GS;
     const int kpad = a.nkb * kKBlockElems;
     uint8_t* xq = smem;                                                  // kpad * ES bytes, permuted
@@ -250,24 +296,24 @@ __global__ void __launch_bounds__(kThreads) gemv_kernel(const GemvArgs a) {
     const int gw = blockIdx.x * kWarps + warp, GW = gridDim.x * kWarps;
 
     // ---- start the weight stream before touching activations: the first DEPTH units of this warp
+    const int units_per_task = TT * a.nkb;
     int n_units = 0;
-    if (gw < a.n_tasks) n_units = ((a.n_tasks - 1 - gw) / GW + 1) * TT * a.nkb;
-    const size_t task_stride = (size_t)GW * TT * a.nkb * T::UNIT_BYTES;
-    const uint8_t* task_base = a.w + (size_t)gw * TT * a.nkb * T::UNIT_BYTES + (size_t)lane * 16;
-    // unit u of this warp: task (u / (TT*nkb)), offset (u % (TT*nkb)) — tracked incrementally
+    if (gw < a.n_tasks) n_units = ((a.n_tasks - 1 - gw) / GW + 1) * units_per_task;
+    const size_t task_jump = ((size_t)GW - 1) * units_per_task * T::UNIT_BYTES;      // from the end of a task to the warp's next
+    const uint8_t* ld_w = a.w + (size_t)gw * units_per_task * T::UNIT_BYTES + (size_t)lane * 16;
+    const uint8_t* ld_s = a.w + (size_t)gw * units_per_task * T::UNIT_BYTES + T::W_BYTES + (size_t)lane * T::GPL * 4;
     UnitRegs<QT, GS> buf[DEPTH];
     int ld_u = 0, ld_in_task = 0;
-    const uint8_t* ld_ptr = task_base;
-    const int units_per_task = TT * a.nkb;
     auto issue_load = [&](UnitRegs<QT, GS>& b) {
         if (ld_u < n_units) {
 #pragma unroll
-            for (int j = 0; j < T::NJ; ++j) b.w[j] = ldg_stream(ld_ptr + j * 512);
+            for (int j = 0; j < T::NJ; ++j) b.w[j] = ldg_stream(ld_w + j * 512);
 #pragma unroll
-            for (int gg = 0; gg < T::GPL; ++gg) b.s[gg] = ldg_stream_f32(ld_ptr - (size_t)lane * 16 + T::W_BYTES + (lane * T::GPL + gg) * 4);
+            for (int gg = 0; gg < T::GPL; ++gg) b.s[gg] = ldg_stream_f32(ld_s + gg * 4);
             ++ld_u;
-            ld_ptr += T::UNIT_BYTES;
-            if (++ld_in_task == units_per_task) { ld_in_task = 0; ld_ptr += task_stride - (size_t)units_per_task * T::UNIT_BYTES; }
+            size_t adv = T::UNIT_BYTES;
+            if (++ld_in_task == units_per_task) { ld_in_task = 0; adv += task_jump; }
+            ld_w += adv; ld_s += adv;
         }
     };
 #pragma unroll
@@ -279,7 +325,7 @@ __global__ void __launch_bounds__(kThreads) gemv_kernel(const GemvArgs a) {
     __syncthreads();
     if (PRO == PRO_RMS_QUANT) {
         for (int i = threadIdx.x; i < K / 4; i += kThreads)
-            reinterpret_cast<float4*>(xf)[i] = reinterpret_cast<const float4*>(a.in)[i];
+            reinterpret_cast<float4*>(xf)[i] = __ldcg(reinterpret_cast<const float4*>(a.in) + i);
         __shared__ float s_r;
         __syncthreads();
         if (warp == 0) {
@@ -297,7 +343,7 @@ __global__ void __launch_bounds__(kThreads) gemv_kernel(const GemvArgs a) {
         }, K, xq, xs, nullptr, nullptr);
     } else if (PRO == PRO_QUANT) {
         const float* in = a.in;
-        quantize_block<QT, GS>([&](int e) { return in[e]; }, K, xq, xs, nullptr, nullptr);
+        quantize_block<QT, GS>([&](int e) { return __ldcg(in + e); }, K, xq, xs, nullptr, nullptr);
     } else {
         if (QT == Q_INT8) {
             const uint8_t* q = reinterpret_cast<const uint8_t*>(a.in_q);
@@ -310,7 +356,7 @@ __global__ void __launch_bounds__(kThreads) gemv_kernel(const GemvArgs a) {
     }
     __syncthreads();
 
-    // ---- stream: each warp walks its row tiles; lanes of a row run the reference's group chain together
+    // ---- stream: each warp walks its row tiles, K-block by K-block
     float acc = 0.0f, acc_first = 0.0f;
     int cu = 0, kb = 0, tt = 0, task = gw;
     const uint4* xq4 = reinterpret_cast<const uint4*>(xq);
@@ -318,34 +364,10 @@ __global__ void __launch_bounds__(kThreads) gemv_kernel(const GemvArgs a) {
 #pragma unroll
         for (int i = 0; i < DEPTH; ++i) {
             if (cu < n_units) {
-                UnitRegs<QT, GS>& b = buf[i];
-                int d[T::GPL];
-#pragma unroll
-                for (int gg = 0; gg < T::GPL; ++gg) d[gg] = 0;
-                const uint4* xk = xq4 + (size_t)kb * (T::KB_BYTES / 16);
-#pragma unroll
-                for (int j = 0; j < T::NJ; ++j) {
-                    const uint4 xv = xk[j * 8 + l];
-                    const int gg = (j * 16) / (GS * T::ES);
-                    d[gg] = dot16<QT>(b.w[j], xv, d[gg]);
-                }
-                float sv[T::GPL], fv[T::GPL];
-#pragma unroll
-                for (int gg = 0; gg < T::GPL; ++gg) {
-                    sv[gg] = __fmul_rn(b.s[gg], xs[(kb * 8 + l) * T::GPL + gg]);   // scales1[..] * *s2  (:274)
-                    fv[gg] = __int2float_rn(d[gg]);
-                }
-                issue_load(b);      // refill this slot before the (latency-bound) chain
-                // o[j] += s * dot  ==  fma(s, (float)dot, o[j]), groups ascending   (:275)
-#pragma unroll
-                for (int l2 = 0; l2 < 8; ++l2) {
-#pragma unroll
-                    for (int gg = 0; gg < T::GPL; ++gg) {
-                        const float sj = __shfl_sync(kFull, sv[gg], (r << 3) + l2);
-                        const float fj = __shfl_sync(kFull, fv[gg], (r << 3) + l2);
-                        if ((kb * 8 + l2) * T::GPL + gg < G) acc = __fmaf_rn(sj, fj, acc);
-                    }
-                }
+                UnitRegs<QT, GS> cur = buf[i];
+                issue_load(buf[i]);          // refill the slot; the loads fly while the chain below runs
+                acc = unit_chain<QT, GS>(cur.w, cur.s, xq4 + (size_t)kb * (T::KB_BYTES / 16), xs + kb * 8 * T::GPL,
+                                         chain_slots[warp][cu & 1], lane, acc);
                 ++cu;
                 if (++kb == a.nkb) {
                     kb = 0;

@@ -77,7 +77,8 @@ typedef struct {
 } fl_config;
 
 #define FL_FLAG_NO_GRAPH   1   /* launch kernels directly instead of replaying the captured CUDA graph */
-#define FL_FLAG_NO_PDL     2   /* disable programmatic dependent launch between the step's kernels */
+#define FL_FLAG_NO_PDL     2   /* reserved */
+#define FL_FLAG_NO_MEGAKERNEL 4 /* run the step as separate kernels (one per phase) instead of the persistent decode kernel */
 
 /* ---- lifecycle ---------------------------------------------------------------------------- */
 int  fl_create(const fl_config* cfg, int device, fl_engine** out);

@@ -44,12 +44,17 @@ CASES = [
 ]
 
 
+# the persistent decode kernel (default), the per-phase kernels replayed as a CUDA graph, and launched directly
+PATHS = [("mega", 0), ("graph", 4), ("direct", 4 | 1)]
+
+
+@pytest.mark.parametrize("path,flags", PATHS, ids=[p[0] for p in PATHS])
 @pytest.mark.parametrize("name,spec,qt,gs,qemb", CASES, ids=[c[0] for c in CASES])
-def test_forward_logits_bit_exact(fl, name, spec, qt, gs, qemb):
+def test_forward_logits_bit_exact(fl, name, spec, qt, gs, qemb, path, flags):
     w = gen_weights(spec, seed=1)
     qm = quantize_model(spec, w, qt, gs, quantize_embedding=qemb)
     pm = make_port_model(spec, qm, qt, gs)
-    eng = make_engine(fl, spec, qm, qt, gs)
+    eng = make_engine(fl, spec, qm, qt, gs, flags=flags)
     P = port()
     toks = prompt_tokens(spec, 6, seed=3)
     want = np.empty(spec.vocab_size, np.float32)
@@ -59,6 +64,8 @@ def test_forward_logits_bit_exact(fl, name, spec, qt, gs, qemb):
         n = C.c_int(0)
         pt = P.port_tap(pm, tap.encode(), spec.n_layers - 1, C.byref(n))
         ref_tap = np.ctypeslib.as_array(pt, (n.value,)).copy()
+        if tap == "qkv" and path == "mega":
+            continue            # the persistent kernel keeps no post-RoPE copy
         gpu_tap = eng.tap(tap)
         assert np.array_equal(bits(gpu_tap), bits(ref_tap)), (name, tap, np.abs(gpu_tap - ref_tap).max())
     assert np.array_equal(bits(got), bits(want)), (name, np.abs(got - want).max())
@@ -94,14 +101,14 @@ def test_generate_greedy_matches_oracle_and_graph_equals_direct(fl):
         want.append(P.port_argmax(ptr(logits), spec.vocab_size))
         pos += 1
     outs = []
-    for flags in (0, fl.FLAG_NO_GRAPH):
+    for flags in (0, fl.FLAG_NO_MEGAKERNEL, fl.FLAG_NO_MEGAKERNEL | fl.FLAG_NO_GRAPH):
         eng = make_engine(fl, spec, qm, qt, gs, flags=flags)
         before = eng.launch_count()
         outs.append(eng.generate_greedy(prompt, n_new))
         assert eng.launch_count() > before
         eng.close()
-    assert outs[0].tolist() == want
-    assert outs[1].tolist() == want
+    for o in outs:
+        assert o.tolist() == want
     P.port_model_free(pm)
 
 
