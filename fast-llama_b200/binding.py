@@ -8,11 +8,11 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 Q_INT16, Q_INT8 = 1, 2
 (T_TOK_EMB, T_ATT_NORM, T_WQ, T_WK, T_WV, T_WO, T_FFN_NORM, T_W1, T_W2, T_W3, T_OUT_NORM, T_CLS) = range(12)
-FLAG_NO_GRAPH, FLAG_NO_PDL, FLAG_NO_MEGAKERNEL = 1, 2, 4
+FLAG_NO_GRAPH, FLAG_NO_PDL, FLAG_NO_MEGAKERNEL, FLAG_PROFILE = 1, 2, 4, 8
 
 EXPORTED_SYMBOLS = [
     "fl_create", "fl_destroy", "fl_last_error", "fl_upload", "fl_finalize", "fl_forward", "fl_forward_batch",
-    "fl_generate_greedy", "fl_decode_async", "fl_stream", "fl_device_ptr", "fl_sync", "fl_launch_count", "fl_step_bytes", "fl_tap",
+    "fl_generate_greedy", "fl_decode_async", "fl_stream", "fl_device_ptr", "fl_profile_read", "fl_sync", "fl_launch_count", "fl_step_bytes", "fl_tap",
     "fl_set_comm", "fl_allgather_tokens", "fl_op_quantize", "fl_op_matmul_q", "fl_op_rmsnorm", "fl_op_rope",
     "fl_op_softmax", "fl_op_swiglu", "fl_op_expf", "fl_op_attn_decode", "fl_op_argmax",
 ]
@@ -60,6 +60,7 @@ def lib():
     L.fl_stream.restype = vp
     L.fl_device_ptr.argtypes = [vp, C.c_char_p, C.c_int]
     L.fl_device_ptr.restype = vp
+    L.fl_profile_read.argtypes = [vp, vp, C.c_int, C.c_int]
     L.fl_sync.argtypes = [vp]
     L.fl_launch_count.argtypes = [vp]
     L.fl_launch_count.restype = C.c_int64
@@ -236,6 +237,11 @@ class Engine:
         if not p:
             raise FlError(f"fl_device_ptr: unknown name {name!r}")
         return p
+
+    def profile_read(self, reset=True):
+        buf = np.zeros(32 * 1024, np.uint64)
+        n = _check(lib().fl_profile_read(self.h, _p(buf), buf.size, int(reset)), self.h)
+        return buf[:n].reshape(-1, 32).copy()
 
     def launch_count(self):
         return lib().fl_launch_count(self.h)

@@ -84,6 +84,7 @@ struct fl_engine {
     unsigned long long* head_ctr = nullptr;
     float* am_val = nullptr;
     int* am_idx = nullptr;
+    unsigned long long* prof = nullptr;
     MegaParams mega{};
     size_t mega_smem = 0;
     bool finalized = false;
@@ -300,19 +301,22 @@ int setup_mega(fl_engine* e) {
         tab[l].att_norm = e->att_norm + (size_t)l * c.dim; tab[l].ffn_norm = e->ffn_norm + (size_t)l * c.dim;
     }
     CK(e, cudaMalloc(&e->mega_layers, sizeof(MegaLayer) * L));
-    CK(e, cudaMemcpy(e->mega_layers, tab.data(), sizeof(MegaLayer) * L, cudaMemcpyHostToDevice));
+    CK(e, cudaMemcpyAsync(e->mega_layers, tab.data(), sizeof(MegaLayer) * L, cudaMemcpyHostToDevice, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
     CK(e, cudaMalloc(&e->att_scratch, (size_t)c.n_heads * c.max_seq_len * 4));
     CK(e, cudaMalloc(&e->bar_ctr, 2 * sizeof(unsigned long long)));
-    CK(e, cudaMemset(e->bar_ctr, 0, 2 * sizeof(unsigned long long)));
+    CK(e, cudaMemsetAsync(e->bar_ctr, 0, 2 * sizeof(unsigned long long), e->stream));   // same stream as the launches
     CK(e, cudaMalloc(&e->head_ctr, 2 * (size_t)c.n_heads * sizeof(unsigned long long)));
-    CK(e, cudaMemset(e->head_ctr, 0, 2 * (size_t)c.n_heads * sizeof(unsigned long long)));
+    CK(e, cudaMemsetAsync(e->head_ctr, 0, 2 * (size_t)c.n_heads * sizeof(unsigned long long), e->stream));
     CK(e, cudaMalloc(&e->am_val, sizeof(float) * e->n_sms));
     CK(e, cudaMalloc(&e->am_idx, sizeof(int) * e->n_sms));
+    CK(e, cudaMalloc(&e->prof, sizeof(unsigned long long) * 32 * e->n_sms));
+    CK(e, cudaMemsetAsync(e->prof, 0, sizeof(unsigned long long) * 32 * e->n_sms, e->stream));
     MegaParams& p = e->mega;
     p.layers = e->mega_layers; p.cls = e->cls.d; p.out_norm = e->out_norm; p.emb = e->emb;
     p.x1 = e->x1; p.qkv = e->qkv_buf; p.attn = e->attn; p.hd = e->hd; p.logits = e->logits; p.att_scratch = e->att_scratch;
     p.rope = e->rope; p.out_cap = e->out_cap;
-    p.bar_ctr = e->bar_ctr; p.head_ctr = e->head_ctr; p.am_val = e->am_val; p.am_idx = e->am_idx; p.tap_norm = e->tap_norm;
+    p.bar_ctr = e->bar_ctr; p.head_ctr = e->head_ctr; p.am_val = e->am_val; p.am_idx = e->am_idx; p.tap_norm = e->tap_norm; p.prof = (c.flags & FL_FLAG_PROFILE) ? e->prof : nullptr;
     p.dim = c.dim; p.hidden = c.hidden_dim; p.n_layers = L; p.n_heads = c.n_heads; p.n_kv_heads = c.n_kv_heads;
     p.vocab = c.vocab_size; p.max_seq = c.max_seq_len; p.qkv_rows = c.dim + 2 * c.head_size * c.n_kv_heads;
     p.attn_scale = 1.0f / sqrtf((float)c.head_size);
@@ -327,7 +331,7 @@ int setup_mega(fl_engine* e) {
     auto al = [](size_t v, size_t a) { return (v + a - 1) / a * a; };
     size_t off = 0;
     p.off_misc = (int)off; off += 2048;
-    p.off_chain = (int)off; off += (size_t)kConsumerWarps * 2 * 32 * 2 * gpl * 4;
+    p.off_chain = (int)off; off += (size_t)kConsumerWarps * (qt == FL_Q_INT8 ? 4 : 2) * 32 * 2 * gpl * 4;   // one stage of (s, f) pairs per warp
     p.off_att = (int)off; off += al((size_t)c.max_seq_len * 4, 128);
     p.off_xs = (int)off; off += al((size_t)nkb_max * 8 * gpl * 4, 128);
     const size_t xq_bytes = (size_t)nkb_max * kKBlockElems * es, xf_bytes = (size_t)c.dim * 4;
@@ -527,7 +531,7 @@ void fl_destroy(fl_engine* e) {
     fr(e->x1); fr(e->qkv_buf); fr(e->attn); fr(e->hd); fr(e->logits); fr(e->tap_qkv); fr(e->tap_norm);
     fr(e->k_cache); fr(e->v_cache); fr(e->rope); fr(e->states); fr(e->out_tokens); fr(e->in_tokens); fr(e->argmax_dev);
     fr(e->ag_send); fr(e->ag_recv);
-    fr(e->mega_layers); fr(e->att_scratch); fr(e->bar_ctr); fr(e->head_ctr); fr(e->am_val); fr(e->am_idx);
+    fr(e->mega_layers); fr(e->att_scratch); fr(e->bar_ctr); fr(e->head_ctr); fr(e->am_val); fr(e->am_idx); fr(e->prof);
     if (e->h_tokens) cudaFreeHost(e->h_tokens);
     if (e->h_logits) cudaFreeHost(e->h_logits);
     if (e->h_argmax) cudaFreeHost(e->h_argmax);
@@ -562,14 +566,16 @@ int fl_upload(fl_engine* e, int kind, int layer, const void* q, const float* sca
     if (kind == FL_T_ATT_NORM || kind == FL_T_FFN_NORM || kind == FL_T_OUT_NORM) {
         float* dst = kind == FL_T_ATT_NORM ? e->att_norm + (size_t)layer * c.dim
                    : kind == FL_T_FFN_NORM ? e->ffn_norm + (size_t)layer * c.dim : e->out_norm;
-        CK(e, cudaMemcpy(dst, q, n * 4, cudaMemcpyHostToDevice));
+        CK(e, cudaMemcpyAsync(dst, q, n * 4, cudaMemcpyHostToDevice, e->stream));
+        CK(e, cudaStreamSynchronize(e->stream));
     } else if (kind == FL_T_TOK_EMB && scales == nullptr) {
-        CK(e, cudaMemcpy(e->emb, q, n * 4, cudaMemcpyHostToDevice));         // .flm keeps fp32 embedding rows
+        CK(e, cudaMemcpyAsync(e->emb, q, n * 4, cudaMemcpyHostToDevice, e->stream));         // .flm keeps fp32 embedding rows
+        CK(e, cudaStreamSynchronize(e->stream));
     } else {
         if (!scales) return set_err(e, FL_ERR_INVALID, "fl_upload: kind %d needs a scale table", kind);
         float* d_scales = reinterpret_cast<float*>(e->staging + ((n * es + 255) & ~(size_t)255));
-        CK(e, cudaMemcpy(e->staging, q, n * es, cudaMemcpyHostToDevice));
-        CK(e, cudaMemcpy(d_scales, scales, n / gs * 4, cudaMemcpyHostToDevice));
+        CK(e, cudaMemcpyAsync(e->staging, q, n * es, cudaMemcpyHostToDevice, e->stream));
+        CK(e, cudaMemcpyAsync(d_scales, scales, n / gs * 4, cudaMemcpyHostToDevice, e->stream));
         if (kind == FL_T_TOK_EMB) {
             // dequantised once here; the reference dequantises the row per token (transformer.cpp:117-118), same bits
             dequant_rows_kernel<<<1024, 256, 0, e->stream>>>(e->staging, d_scales, e->emb, n, gs, qt);
@@ -615,13 +621,15 @@ int fl_finalize(fl_engine* e) {
     std::vector<float> tab;
     build_rope_table(tab, c.max_seq_len * hgs + 1, c.head_size);   // q positions reach pos + g*bs (GQA quirk)
     CK(e, cudaMalloc(&e->rope, tab.size() * 4));
-    CK(e, cudaMemcpy(e->rope, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
+    CK(e, cudaMemcpyAsync(e->rope, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
     if (e->staging) { cudaFree(e->staging); e->staging = nullptr; }
     if (!(c.flags & FL_FLAG_NO_MEGAKERNEL)) {
         int rc = setup_mega(e);
         if (rc) return rc;
         e->use_mega = true;
     }
+    CK(e, cudaStreamSynchronize(e->stream));
     e->finalized = true;
     return FL_OK;
 }
@@ -725,6 +733,18 @@ int fl_sync(fl_engine* e) {
 
 int64_t fl_launch_count(const fl_engine* e) { return e ? e->launches : 0; }
 
+int fl_profile_read(fl_engine* e, uint64_t* out, int cap, int reset) {
+    if (!e || !out || !e->prof) return set_err(e, FL_ERR_INVALID, "fl_profile_read: profiling not enabled (FL_FLAG_PROFILE) or null argument");
+    const int n = 32 * e->n_sms;
+    if (cap < n) return set_err(e, FL_ERR_INVALID, "fl_profile_read: buffer too small (%d < %d)", cap, n);
+    CK(e, cudaSetDevice(e->device));
+    CK(e, cudaStreamSynchronize(e->stream));
+    CK(e, cudaMemcpyAsync(out, e->prof, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    if (reset) { CK(e, cudaMemsetAsync(e->prof, 0, sizeof(uint64_t) * n, e->stream)); CK(e, cudaStreamSynchronize(e->stream)); }
+    return n;
+}
+
 void* fl_device_ptr(fl_engine* e, const char* name, int seq_slot) {
     if (!e || !name || seq_slot < 0 || seq_slot >= e->c.max_seqs) return nullptr;
     if (!strcmp(name, "token")) return &e->states[seq_slot].token;          // int32: input token of the next step
@@ -762,7 +782,8 @@ int fl_tap(fl_engine* e, const char* name, float* out, int cap) {
     if (cap < n) return set_err(e, FL_ERR_INVALID, "fl_tap: buffer too small (%d < %d)", cap, n);
     CK(e, cudaSetDevice(e->device));
     CK(e, cudaStreamSynchronize(e->stream));
-    CK(e, cudaMemcpy(out, src, sizeof(float) * n, cudaMemcpyDeviceToHost));
+    CK(e, cudaMemcpyAsync(out, src, sizeof(float) * n, cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
     return n;
 }
 

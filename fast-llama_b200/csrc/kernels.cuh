@@ -107,9 +107,11 @@ __global__ void pack_weights_kernel(const uint8_t* __restrict__ raw, const float
 __device__ __forceinline__ float sumsq_chain_warp0(const float* xf, int n, int lane) {
     float acc = 0.0f;
     if (lane < 4) {
+        // FFMA-latency bound (profiles/micro/chain_bench.cu: 6.2 cycles per step on B200; deeper software pipelining is slower)
         const float* p = xf + lane;
         int i = 0;
         const int steps = n / 4;
+#pragma unroll 1
         for (; i + 8 <= steps; i += 8) {
             float v[8];
 #pragma unroll

@@ -78,6 +78,7 @@ typedef struct {
 
 #define FL_FLAG_NO_GRAPH   1   /* launch kernels directly instead of replaying the captured CUDA graph */
 #define FL_FLAG_NO_PDL     2   /* reserved */
+#define FL_FLAG_PROFILE    8   /* persistent kernel records per-CTA time per category (fl_profile_read) */
 #define FL_FLAG_NO_MEGAKERNEL 4 /* run the step as separate kernels (one per phase) instead of the persistent decode kernel */
 
 /* ---- lifecycle ---------------------------------------------------------------------------- */
@@ -117,6 +118,12 @@ int   fl_sync(fl_engine* e);
 /* device addresses of per-slot state for zero-copy consumers on the engine stream (e.g. an NCCL all-gather of the
  * sampled token): name in {"token","pos","argmax","out_tokens","logits"}; NULL if unknown. */
 void* fl_device_ptr(fl_engine* e, const char* name, int seq_slot);
+/* per-CTA nanoseconds spent per category by the persistent decode kernel since the last reset:
+ * out[cta*32 + k], k = 0 grid barriers, 1 activation rebuild tail (after the rmsnorm chain / whole quantise), 2 QKV, 3 Wo,
+ * 4 W1/W3, 5 W2, 6 classifier, 7 attention tail, 8 rebuild: loads + pre-products, 9 rebuild: sum-of-squares chain,
+ * 10 attention: RoPE/append, 11 QK^T, 12 score exchange, 13 softmax, 14-17 PV (wait for V chunk, chain, issue next chunk, tail).  Needs FL_FLAG_PROFILE.
+ * Returns the element count (32 * n_CTAs). */
+int  fl_profile_read(fl_engine* e, uint64_t* out, int cap, int reset);
 /* number of kernels this engine has launched (graph nodes count once per replay) */
 int64_t fl_launch_count(const fl_engine* e);
 /* algorithmic bytes one decode step at context length `ctx` must read/write (weights + scales + KV), SURVEY §8d */

@@ -1,0 +1,28 @@
+"""Per-category time inside the persistent decode kernel (FL_FLAG_PROFILE), LLaMA2-7B-shaped INT8."""
+import os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import __graft_entry__ as ge
+from bench import synth_int8_model, shape_7b
+fl = ge._pkg()
+spec = shape_7b()
+ctx = int(sys.argv[1]) if len(sys.argv) > 1 else 288
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 64
+eng = fl.Engine(spec.dim, spec.hidden_dim, spec.n_layers, spec.n_heads, spec.n_kv_heads, spec.vocab_size, max_seq_len=1024, flags=fl.FLAG_PROFILE)
+for (kind, layer), (q, s) in synth_int8_model(spec, 0):
+    eng.upload(kind, layer, q, s)
+eng.finalize()
+tok = np.array([5], np.int32)
+eng.forward(tok, ctx - 2, want_logits=False)
+eng.profile_read(reset=True)
+import time
+t0 = time.perf_counter(); eng.decode_async(steps); eng.sync(); dt = time.perf_counter() - t0
+pr = eng.profile_read().astype(np.float64) / steps / 1e3     # us per token per CTA
+names = ["grid_barrier", "build_tail", "qkv", "wo", "w13", "w2", "cls", "attn_tail", "build_load", "build_chain", "attn_rope", "attn_qk", "attn_xchg", "attn_softmax", "pv_wait", "pv_chain", "pv_issue", "pv_tail"] + ["-"] * 14
+print(f"ctx {ctx}: {dt / steps * 1e3:.3f} ms/token (host clock), {steps} steps")
+print(f"{'category':14s} {'mean':>9s} {'min':>9s} {'max':>9s}   (us per token, over {pr.shape[0]} CTAs)")
+for k, n in enumerate(names):
+    if n == '-': continue
+    print(f"{n:14s} {pr[:, k].mean():9.1f} {pr[:, k].min():9.1f} {pr[:, k].max():9.1f}")
+print(f"{'sum':14s} {pr.sum(1).mean():9.1f} {pr.sum(1).min():9.1f} {pr.sum(1).max():9.1f}")
