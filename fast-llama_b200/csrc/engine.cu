@@ -78,12 +78,11 @@ struct fl_engine {
     std::vector<cudaGraphExec_t> graphs;
     // megakernel state
     bool use_mega = false;
+    int cph = 1;                        // CTAs per head in the persistent kernel; also the column blocking of the V cache
     MegaLayer* mega_layers = nullptr;
-    float* att_scratch = nullptr;
-    unsigned long long* bar_ctr = nullptr;
-    unsigned long long* head_ctr = nullptr;
-    float* am_val = nullptr;
-    int* am_idx = nullptr;
+    uint2 *x1t = nullptr, *qkvt = nullptr, *attnt = nullptr, *hdt = nullptr, *score_t = nullptr;   // tagged exchange buffers
+    uint4* am = nullptr;
+    uint32_t epoch = 0;                 // last tag handed out (see megakernel.cuh)
     unsigned long long* prof = nullptr;
     MegaParams mega{};
     size_t mega_smem = 0;
@@ -238,6 +237,7 @@ int enqueue_step(fl_engine* e, int slot, cudaStream_t st, int* n_kernels) {
         a.tap_qkv = (l == c.n_layers - 1) ? e->tap_qkv : nullptr;
         a.n_heads = c.n_heads; a.n_kv_heads = c.n_kv_heads; a.max_seq = c.max_seq_len;
         a.attn_scale = 1.0f / sqrtf((float)c.head_size);
+        a.v_dw = c.head_size / e->cph;
         rc = launch_attn(e, c.head_size, a, c.max_seq_len, st);
         if (rc) return rc;
         ++nk;
@@ -303,42 +303,55 @@ int setup_mega(fl_engine* e) {
     CK(e, cudaMalloc(&e->mega_layers, sizeof(MegaLayer) * L));
     CK(e, cudaMemcpyAsync(e->mega_layers, tab.data(), sizeof(MegaLayer) * L, cudaMemcpyHostToDevice, e->stream));
     CK(e, cudaStreamSynchronize(e->stream));
-    CK(e, cudaMalloc(&e->att_scratch, (size_t)c.n_heads * c.max_seq_len * 4));
-    CK(e, cudaMalloc(&e->bar_ctr, 2 * sizeof(unsigned long long)));
-    CK(e, cudaMemsetAsync(e->bar_ctr, 0, 2 * sizeof(unsigned long long), e->stream));   // same stream as the launches
-    CK(e, cudaMalloc(&e->head_ctr, 2 * (size_t)c.n_heads * sizeof(unsigned long long)));
-    CK(e, cudaMemsetAsync(e->head_ctr, 0, 2 * (size_t)c.n_heads * sizeof(unsigned long long), e->stream));
-    CK(e, cudaMalloc(&e->am_val, sizeof(float) * e->n_sms));
-    CK(e, cudaMalloc(&e->am_idx, sizeof(int) * e->n_sms));
+    const int qkv_rows = c.dim + 2 * c.head_size * c.n_kv_heads;
+    const int score_stride = (c.max_seq_len + 3) & ~1;
+    auto alloc_tagged = [&](uint2** ptr, size_t words) -> int {
+        CK(e, cudaMalloc(ptr, (words + 2) * sizeof(uint2)));
+        CK(e, cudaMemsetAsync(*ptr, 0, (words + 2) * sizeof(uint2), e->stream));      // tag 0 is never used
+        return FL_OK;
+    };
+    if (int rc = alloc_tagged(&e->x1t, c.dim)) return rc;
+    if (int rc = alloc_tagged(&e->qkvt, qkv_rows)) return rc;
+    if (int rc = alloc_tagged(&e->attnt, c.dim)) return rc;
+    if (int rc = alloc_tagged(&e->hdt, c.hidden_dim)) return rc;
+    if (int rc = alloc_tagged(&e->score_t, (size_t)c.n_heads * score_stride)) return rc;
+    CK(e, cudaMalloc(&e->am, sizeof(uint4) * e->n_sms));
+    CK(e, cudaMemsetAsync(e->am, 0, sizeof(uint4) * e->n_sms, e->stream));
     CK(e, cudaMalloc(&e->prof, sizeof(unsigned long long) * 32 * e->n_sms));
     CK(e, cudaMemsetAsync(e->prof, 0, sizeof(unsigned long long) * 32 * e->n_sms, e->stream));
     MegaParams& p = e->mega;
     p.layers = e->mega_layers; p.cls = e->cls.d; p.out_norm = e->out_norm; p.emb = e->emb;
-    p.x1 = e->x1; p.qkv = e->qkv_buf; p.attn = e->attn; p.hd = e->hd; p.logits = e->logits; p.att_scratch = e->att_scratch;
-    p.rope = e->rope; p.out_cap = e->out_cap;
-    p.bar_ctr = e->bar_ctr; p.head_ctr = e->head_ctr; p.am_val = e->am_val; p.am_idx = e->am_idx; p.tap_norm = e->tap_norm; p.prof = (c.flags & FL_FLAG_PROFILE) ? e->prof : nullptr;
+    p.x1t = e->x1t; p.qkvt = e->qkvt; p.attnt = e->attnt; p.hdt = e->hdt; p.score_t = e->score_t; p.am = e->am; p.logits = e->logits;
+    p.rope = e->rope; p.out_cap = e->out_cap; p.score_stride = score_stride;
+    p.tap_norm = e->tap_norm; p.prof = (c.flags & FL_FLAG_PROFILE) ? e->prof : nullptr;
     p.dim = c.dim; p.hidden = c.hidden_dim; p.n_layers = L; p.n_heads = c.n_heads; p.n_kv_heads = c.n_kv_heads;
-    p.vocab = c.vocab_size; p.max_seq = c.max_seq_len; p.qkv_rows = c.dim + 2 * c.head_size * c.n_kv_heads;
+    p.vocab = c.vocab_size; p.max_seq = c.max_seq_len; p.qkv_rows = qkv_rows;
     p.attn_scale = 1.0f / sqrtf((float)c.head_size);
-    int cph = 4;
-    while (cph > 1 && (c.n_heads * cph > e->n_sms || c.head_size / cph < 16)) cph /= 2;
+    const int cph = e->cph;
     if (c.n_heads > e->n_sms) return set_err(e, FL_ERR_UNSUPPORTED, "megakernel: n_heads %d > SM count %d", c.n_heads, e->n_sms);
+    if (c.dim > 6144) return set_err(e, FL_ERR_UNSUPPORTED, "megakernel: dim %d > 6144 (the rmsnorm rebuild keeps the vector in registers)", c.dim);
     p.cph = cph;
     const int dw = c.head_size / cph;
-    p.v_chunk_rows = 2048 / dw;
+    p.v_chunk_rows = 1024 / dw;                     // V chunks of 4 KB
     // shared memory carve-up
     const int nkb_max = ceil_div(c.dim > c.hidden_dim ? c.dim : c.hidden_dim, kKBlockElems);
     auto al = [](size_t v, size_t a) { return (v + a - 1) / a * a; };
     size_t off = 0;
     p.off_misc = (int)off; off += 2048;
-    p.off_chain = (int)off; off += (size_t)kConsumerWarps * (qt == FL_Q_INT8 ? 4 : 2) * 32 * 2 * gpl * 4;   // one stage of (s, f) pairs per warp
-    p.off_att = (int)off; off += al((size_t)c.max_seq_len * 4, 128);
+    p.off_att = (int)off; off += al((size_t)c.max_seq_len * 4 + 64, 128);
     p.off_xs = (int)off; off += al((size_t)nkb_max * 8 * gpl * 4, 128);
-    const size_t xq_bytes = (size_t)nkb_max * kKBlockElems * es, xf_bytes = (size_t)c.dim * 4;
-    size_t scratch = xq_bytes + xf_bytes;
-    const size_t vneed = 3 * (size_t)p.v_chunk_rows * dw * 4;
-    if (scratch < vneed) scratch = vneed;
-    p.off_xq = (int)off; p.off_vstage = (int)off; p.off_xf = (int)(off + xq_bytes); off += al(scratch, 128);
+    p.off_vbars = (int)off; off += 128;
+    // [chain slots | activation image | transposed fp32 vector]: contiguous, because attention (which uses none of them)
+    // turns the whole range into its ring of V chunks
+    const size_t chain_bytes = (size_t)kConsumerWarps * (qt == FL_Q_INT8 ? 4 : 2) * 32 * 2 * gpl * 4;   // one stage of (s, f) pairs per warp
+    const size_t xq_bytes = al((size_t)nkb_max * kKBlockElems * es, 128), xt_bytes = al((size_t)c.dim * 4, 128);
+    p.off_vstage = (int)off;
+    p.off_chain = (int)off; off += chain_bytes;
+    p.off_xq = (int)off; off += xq_bytes;
+    p.off_xt = (int)off; off += xt_bytes;
+    size_t vbytes = off - p.off_vstage;
+    if (vbytes < 2 * 4096) { off += 2 * 4096 - vbytes; vbytes = 2 * 4096; }
+    p.n_vchunks = (int)(vbytes / 4096) > 16 ? 16 : (int)(vbytes / 4096);
     int max_smem = 0;
     CK(e, cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, e->device));
     const size_t slot_bytes = (size_t)(qt == FL_Q_INT8 ? 4 : 2) * unit_bytes(qt, gs);
@@ -346,6 +359,8 @@ int setup_mega(fl_engine* e) {
     if (n_slots > 32) n_slots = 32;
     if (n_slots < 4) return set_err(e, FL_ERR_UNSUPPORTED, "megakernel: not enough shared memory for the weight ring (%d slots)", n_slots);
     p.n_slots = n_slots;
+    p.window = 99;
+    if (const char* w = getenv("FL_WINDOW")) { const int v = atoi(w); if (v >= 1) p.window = v; }      // tuning knob (profiles/)
     p.off_bars = (int)off; off += al((size_t)n_slots * 16, 128);
     p.off_ring = (int)off; off += (size_t)n_slots * slot_bytes;
     e->mega_smem = off;
@@ -371,6 +386,8 @@ int launch_mega(fl_engine* e, int slot, int n_steps) {
     p.out_tokens = e->out_tokens + (size_t)slot * e->out_cap;
     p.argmax_out = e->argmax_dev + slot;
     p.n_steps = n_steps;
+    p.epoch = e->epoch;
+    e->epoch += (uint32_t)n_steps * (uint32_t)(c.n_layers + 1) * kTagsPerLayer;
     return dispatch_mega(c.quant_type, c.group_size, c.head_size, [&](auto kern) -> int {
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(e->n_sms); cfg.blockDim = dim3(kMegaThreads); cfg.dynamicSmemBytes = e->mega_smem; cfg.stream = e->stream;
@@ -463,6 +480,8 @@ int fl_create(const fl_config* cfg, int device, fl_engine** out) {
     CKF(cudaGetDeviceProperties(&prop, device));
     e->n_sms = prop.multiProcessorCount;
     CKF(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    e->cph = 4;
+    while (e->cph > 1 && (c.n_heads * e->cph > e->n_sms || c.head_size / e->cph < 16)) e->cph /= 2;
 
     const int L = c.n_layers, kv_dim = c.head_size * c.n_kv_heads;
     e->have.assign((size_t)FL_T__COUNT * L, 0);
@@ -531,7 +550,7 @@ void fl_destroy(fl_engine* e) {
     fr(e->x1); fr(e->qkv_buf); fr(e->attn); fr(e->hd); fr(e->logits); fr(e->tap_qkv); fr(e->tap_norm);
     fr(e->k_cache); fr(e->v_cache); fr(e->rope); fr(e->states); fr(e->out_tokens); fr(e->in_tokens); fr(e->argmax_dev);
     fr(e->ag_send); fr(e->ag_recv);
-    fr(e->mega_layers); fr(e->att_scratch); fr(e->bar_ctr); fr(e->head_ctr); fr(e->am_val); fr(e->am_idx); fr(e->prof);
+    fr(e->mega_layers); fr(e->x1t); fr(e->qkvt); fr(e->attnt); fr(e->hdt); fr(e->score_t); fr(e->am); fr(e->prof);
     if (e->h_tokens) cudaFreeHost(e->h_tokens);
     if (e->h_logits) cudaFreeHost(e->h_logits);
     if (e->h_argmax) cudaFreeHost(e->h_argmax);
@@ -782,6 +801,20 @@ int fl_tap(fl_engine* e, const char* name, float* out, int cap) {
     if (cap < n) return set_err(e, FL_ERR_INVALID, "fl_tap: buffer too small (%d < %d)", cap, n);
     CK(e, cudaSetDevice(e->device));
     CK(e, cudaStreamSynchronize(e->stream));
+    const uint2* tagged = nullptr;       // the persistent kernel keeps these vectors as (value, tag) words
+    if (e->use_mega) {
+        if (!strcmp(name, "x1")) tagged = e->x1t;
+        else if (!strcmp(name, "attn")) tagged = e->attnt;
+        else if (!strcmp(name, "hd")) tagged = e->hdt;
+        else if (!strcmp(name, "qkv")) return set_err(e, FL_ERR_UNSUPPORTED, "fl_tap: the persistent kernel keeps no post-RoPE qkv copy");
+    }
+    if (tagged) {
+        std::vector<uint2> tmp(n);
+        CK(e, cudaMemcpyAsync(tmp.data(), tagged, sizeof(uint2) * n, cudaMemcpyDeviceToHost, e->stream));
+        CK(e, cudaStreamSynchronize(e->stream));
+        for (int i = 0; i < n; ++i) memcpy(out + i, &tmp[i].x, 4);
+        return n;
+    }
     CK(e, cudaMemcpyAsync(out, src, sizeof(float) * n, cudaMemcpyDeviceToHost, e->stream));
     CK(e, cudaStreamSynchronize(e->stream));
     return n;
@@ -969,7 +1002,7 @@ int fl_op_attn_decode(int n_heads, int n_kv_heads, int head_size, int pos, const
     AttnArgs a{};
     a.qkv = dqkv.as<float>(); a.k_cache = dk.as<float>(); a.v_cache = dv.as<float>(); a.rope = dtab.as<float>();
     a.pos_ptr = dpos.as<int>(); a.bs_ptr = dbs.as<int>(); a.out = dout.as<float>(); a.tap_qkv = nullptr;
-    a.n_heads = n_heads; a.n_kv_heads = n_kv_heads; a.max_seq = max_seq; a.attn_scale = 1.0f / sqrtf((float)hs);
+    a.n_heads = n_heads; a.n_kv_heads = n_kv_heads; a.max_seq = max_seq; a.attn_scale = 1.0f / sqrtf((float)hs); a.v_dw = hs;
     int rc = launch_attn(nullptr, hs, a, max_seq, 0);
     if (rc) return rc;
     CKO(cudaDeviceSynchronize());

@@ -409,7 +409,7 @@ __global__ void embed_kernel(const float* __restrict__ table, const int* __restr
 struct AttnArgs {
     const float* qkv;      // [dim + 2*kv_dim] fp32 (q | k | v), pre-RoPE
     float* k_cache;        // this layer, this sequence: [n_kv_heads][max_seq][HS] (permuted rows)
-    float* v_cache;        // [n_kv_heads][max_seq][HS]
+    float* v_cache;        // [n_kv_heads][HS / v_dw][max_seq][v_dw]: head dims in column blocks of v_dw (v_dw == HS: natural rows)
     const float* rope;     // [max_pos][HS/2][2] = (cos, sin) built on the host with glibc sincosf
     const int* pos_ptr;    // device: position of the new token
     const int* bs_ptr;     // device: tokens in the enclosing forward() call
@@ -417,6 +417,7 @@ struct AttnArgs {
     float* tap_qkv;        // optional: [dim + 2 kv_dim] post-RoPE copy
     int n_heads, n_kv_heads, max_seq;
     float attn_scale;      // 1/sqrtf(HS) computed on the host (transformer.cpp:416)
+    int v_dw;              // column-block width of the V cache (the persistent kernel streams one block per CTA)
 };
 
 constexpr int kVChunk = 64;    // V rows per cp.async stage
@@ -454,8 +455,10 @@ __global__ void __launch_bounds__(kThreads) attn_decode_kernel(const AttnArgs a)
         const int t0 = c * kVChunk;
         float* dst = v_stage + (size_t)(c & 1) * kVChunk * HS;
         const int rows = min(kVChunk, pos - t0);           // cached rows only (row `pos` comes from v_s)
-        for (int i = tid; i < rows * (HS / 4); i += kThreads)
-            cp_async16(dst + (size_t)i * 4, vc + (size_t)t0 * HS + (size_t)i * 4);
+        for (int i = tid; i < rows * (HS / 4); i += kThreads) {
+            const int row = i / (HS / 4), d = (i - row * (HS / 4)) * 4;
+            cp_async16(dst + (size_t)i * 4, vc + ((size_t)(d / a.v_dw) * a.max_seq + t0 + row) * a.v_dw + d % a.v_dw);
+        }
         cp_async_commit();
     };
     const int n_chunks = ceil_div(n, kVChunk);
@@ -491,7 +494,7 @@ __global__ void __launch_bounds__(kThreads) attn_decode_kernel(const AttnArgs a)
         const float4 v = reinterpret_cast<const float4*>(a.qkv + dim + kv_dim + (size_t)kvh * HS)[i];
         reinterpret_cast<float4*>(v_s)[i] = v;
         if (g == 0) {
-            reinterpret_cast<float4*>(vc + (size_t)pos * HS)[i] = v;
+            *reinterpret_cast<float4*>(vc + ((size_t)((4 * i) / a.v_dw) * a.max_seq + pos) * a.v_dw + (4 * i) % a.v_dw) = v;
             if (a.tap_qkv) reinterpret_cast<float4*>(a.tap_qkv + dim + kv_dim + (size_t)kvh * HS)[i] = v;
         }
     }

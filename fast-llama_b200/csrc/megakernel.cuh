@@ -1,28 +1,37 @@
-// megakernel.cuh — the decode step as ONE persistent sm_100a kernel (one CTA per SM).
+// megakernel.cuh — the decode step as ONE persistent sm_100a kernel (one CTA per SM, no grid barriers).
 //
-// Why: a decode token is 161 dependent matrix-vector phases of 18-140 MB each.  Launched as separate kernels
-// every phase pays launch latency, a cold pipeline and its activation prologue (for rmsnorm a 1024-step serial FP32
-// chain) with HBM idle.  Here the weight stream never stops:
+// Why: a decode token is 161 dependent matrix-vector phases of 18-140 MB each.  Launched as separate kernels every
+// phase pays launch latency, a cold pipeline and its activation prologue with HBM idle.  Here the weight stream never
+// stops:
 //
 //   * warp 8 (one elected lane) is a TMA producer: it walks the token's static weight schedule and issues
 //     cp.async.bulk global->shared copies into a ring of stages guarded by full/empty mbarriers.  Weights do not
-//     depend on activations, so the producer runs ahead across phase, layer and token boundaries; only ring
-//     capacity (~180 KB per SM = ~4 us of this SM's HBM share) limits it.
-//   * warps 0-7 are consumers: per phase they (1) pass a grid-wide barrier, (2) rebuild the quantised activation
-//     vector in shared memory (rmsnorm chain, quantise), (3) drain their stages with the exact per-unit arithmetic
-//     of kernels.cuh and (4) write their rows.  While they do (1)+(2) the ring fills, so HBM stays busy.
-//   * attention runs between the QKV and Wo phases on n_heads * CPH CTAs (CPH CTAs share one head: keys are split
-//     for QK^T, head dims are split for the PV chains), exchanging the score vector through L2.
+//     depend on activations, so the producer runs ahead across phase, layer and token boundaries; only ring capacity
+//     (~180 KB per SM = ~4 us of this SM's HBM share) limits it.  A serial section shorter than that costs nothing.
+//   * warps 0-7 are consumers: per phase they (1) fetch the phase's input vector, (2) rebuild the quantised activation
+//     image in shared memory (rmsnorm chain, quantise), (3) drain their stages with the exact per-unit arithmetic of
+//     kernels.cuh and (4) publish their rows.
+//   * CTAs exchange activations as TAGGED WORDS (value, tag) written and read with single 8-byte accesses, tag = a
+//     number unique to (launch, token, layer, producer phase).  A reader issues all its loads at once and re-issues only
+//     those whose tag is stale, so "wait for every producer" and "fetch the vector" are ONE L2 round trip instead of
+//     barrier (two dependent round trips) + load (a third); profiles/r01/sync_bench_ABD.log has the measurements.
+//     Write-after-read safety needs no extra synchronisation: a buffer is only overwritten by a phase that (transitively)
+//     consumed data from every CTA produced AFTER that CTA's last read of the buffer (DESIGN.md "Tagged exchange").
+//   * attention runs between the QKV and Wo phases on n_heads * CPH CTAs (CPH CTAs share one head: keys are split for
+//     QK^T, head dims are split for the PV chains), exchanging the score vector through L2 the same way.
 //
 // Each CTA owns a contiguous range of 4-row tiles of every matrix (rows/148 +- 4), so its share of a phase is ONE
 // contiguous byte range of the streaming layout and every stage is a single bulk copy.
 //
-// Two hardware facts shape the code (both measured, see DESIGN.md "What the profiler taught us"):
+// Hardware facts that shape the code (all measured, see DESIGN.md "What the profiler taught us"):
 //   1. With ~227 KB of shared memory carved out there is practically no L1 left: every local-memory (stack) access and
-//      every re-read of a global word is an L2 round trip (~0.3 us).  Nothing here may spill or take the address of a
-//      local; everything is force-inlined, parameters stay in the constant bank, loops keep state in registers.
-//   2. The kernel body must stay small: code that runs once per phase is fetched from L2 when it does not fit the
-//      instruction cache.  Hence ONE instance of each phase routine inside a flat, rolled loop over phases.
+//      every re-read of a global word is an L2 round trip.  Nothing here may spill or take the address of a local.
+//   2. The kernel body must stay small (instruction cache): ONE instance of each phase routine inside a flat, rolled loop.
+//   3. An L2 round trip costs 0.3 us on an idle chip and 1-1.5 us while the weight stream saturates HBM; dependent round
+//      trips are what a serial section is made of, so every one of them is counted.
+//   4. A consumer may only wait on a ring slot whose stage has already been issued: mbarrier waits are by phase PARITY, and
+//      a wait for revolution k+1 on a slot still filling for revolution k succeeds spuriously (found with
+//      profiles/micro/sync_bench.cu).  The producer publishes its issue count; consumers check it first.
 #pragma once
 #include "kernels.cuh"
 
@@ -31,6 +40,8 @@ namespace fl {
 constexpr int kConsumerWarps = 8;
 constexpr int kConsumerThreads = kConsumerWarps * 32;
 constexpr int kMegaThreads = kConsumerThreads + 32;
+constexpr int kTagsPerLayer = 8;
+constexpr int kProfThread = 31;       // keeps the profiling clock: last lane of warp 0 (in every GEMV round and in the PV group, not a chain lane)
 
 struct MegaLayer {
     const uint8_t* qkv;
@@ -46,26 +57,28 @@ struct MegaParams {
     const uint8_t* cls;
     const float* out_norm;
     const float* emb;
-    float* x1; float* qkv; float* attn; float* hd; float* logits;
-    float* att_scratch;               // [n_heads][max_seq] raw scores exchanged between the CTAs of a head
+    uint2* x1t; uint2* qkvt; uint2* attnt; uint2* hdt;   // tagged activation vectors: word i = (float bits, tag)
+    uint2* score_t;                   // [n_heads][score_stride] tagged raw scores exchanged between the CTAs of a head
+    uint4* am;                        // [gridDim] argmax partials (value bits, tag, index, tag)
+    float* logits;
     float* k_cache; float* v_cache;   // this sequence: [n_layers][n_kv_heads][max_seq][HS]
     const float* rope;
     SeqState* st;
     int* out_tokens; int out_cap; int* argmax_out;
-    unsigned long long* bar_ctr;      // [0] grid barrier counter, [1] its value at the end of the previous launch
-    unsigned long long* head_ctr;     // [n_heads] per-head arrival counters, [n_heads .. 2 n_heads) their launch bases
-    float* am_val; int* am_idx;       // [gridDim] per-CTA argmax partials
     float* tap_norm;
     unsigned long long* prof;         // optional [gridDim][32] ns per category, see fl_profile_read
     int dim, hidden, n_layers, n_heads, n_kv_heads, vocab, max_seq;
     int qkv_rows;
+    int score_stride;
     float attn_scale;
     int n_steps;
     int cph;                          // CTAs per head (1, 2 or 4)
     int n_slots;                      // ring stages
+    int window;                       // max stages in flight (issued, not yet landed); >= n_slots: no limit
+    uint32_t epoch;                   // tags of this launch are epoch + 1 ... epoch + n_steps * (n_layers + 1) * 8
     // dynamic shared memory carve-up (byte offsets)
-    int off_ring, off_xq, off_xs, off_xf, off_chain, off_att, off_misc, off_bars, off_vstage;
-    int v_chunk_rows;
+    int off_ring, off_xq, off_xs, off_xt, off_chain, off_att, off_misc, off_bars, off_vstage, off_vbars;
+    int v_chunk_rows, n_vchunks;     // V ring of the attention part: n_vchunks chunks of v_chunk_rows rows x HS/cph floats
 };
 
 // ---------------------------------------------------------------------------------------------- PTX helpers
@@ -90,50 +103,61 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 // Producer-side wait: back off instead of spinning, the ring holds microseconds of data.
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
-    while (!mbar_try(bar, parity)) __nanosleep(64);
+    while (!mbar_try(bar, parity)) __nanosleep(32);
 }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" :: "n"(kConsumerThreads) : "memory"); }
-__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void red_release_add_u64(unsigned long long* p, unsigned long long v) {
-    asm volatile("red.release.gpu.global.add.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
-}
 __device__ __forceinline__ unsigned long long gtimer() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
+__device__ __forceinline__ uint32_t ld_shared_volatile_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_shared_volatile_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.volatile.shared.u32 [%0], %1;" :: "r"(smem_u32(p)), "r"(v) : "memory");
+}
 
-// per-CTA phase timing, only when MegaParams::prof is set; lives in registers.  The LAST consumer thread keeps the
-// clock: it takes part in none of the serial single-warp sections (thread 0 timing them made lane 0 diverge from the
-// other chain lanes and doubled their cost), and every stop sits right after a consumer_sync, so it still sees
-// every interval end.
+// ---- tagged words: one 8-byte (value, tag) pair per element; single-copy atomic, so no fences are involved.
+__device__ __forceinline__ uint4 ld_tag2(const uint2* p) {        // two consecutive tagged words (16-byte aligned)
+    uint4 v;
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint2 ld_tag1(const uint2* p) {
+    uint2 v;
+    asm volatile("ld.relaxed.gpu.global.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_tag(uint2* p, float v, uint32_t tag) {
+    asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1,%2};" :: "l"(p), "r"(__float_as_uint(v)), "r"(tag) : "memory");
+}
+__device__ __forceinline__ uint4 ld_relaxed_v4(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_v4(uint4* p, uint4 v) {
+    asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// per-CTA phase timing, only when MegaParams::prof is set; lives in registers.  Thread kProfThread keeps the clock.
 struct Prof {
-    unsigned long long* p; unsigned long long t0;
+    unsigned long long* p; unsigned long long t0; int trace_slot;   // trace_slot >= 0: the current build records when its input was complete
     __device__ __forceinline__ void stop(int tid, int cat) {
-        if (p && tid == kConsumerThreads - 1) { const unsigned long long t = gtimer(); atomicAdd(p + cat, t - t0); t0 = t; }
+        if (p && tid == kProfThread) { const unsigned long long t = gtimer(); atomicAdd(p + cat, t - t0); t0 = t; }
+    }
+    // absolute timestamp of one event of the traced layer (slots 20..31): skew and latency of one exchange, see profiles/trace_layer.py
+    __device__ __forceinline__ void mark(int tid, int slot, bool on) {
+        if (p && on && tid == kProfThread) p[slot] = gtimer();
     }
 };
-
-// grid-wide barrier for the consumer warps of all CTAs (all CTAs are co-resident: cooperative launch).
-// bar.sync makes every consumer thread's stores happen-before thread 0's release; the acquire poll + bar.sync make the
-// other CTAs' stores visible to every consumer thread (which then read them with L2 loads, never through L1).
-__device__ __forceinline__ void grid_barrier(unsigned long long* ctr, unsigned long long& target, int tid) {
-    consumer_sync();
-    if (tid == 0) {
-        red_release_add_u64(ctr, 1ull);
-        while (ld_acquire_u64(ctr) < target) { }
-    }
-    consumer_sync();
-    target += gridDim.x;
-}
 
 // ---------------------------------------------------------------------------------------------- schedule
 template <int QT, int GS>
@@ -205,75 +229,173 @@ __device__ __forceinline__ void quant_store(uint8_t* xq, float* xs, const float 
     }
 }
 
-// Rebuild the quantised activation vector of a phase in shared memory (every CTA, redundantly).
+// simd::rmsnorm's sum of squares (x86_simd.cpp:941-962 via the __AVX2 typo at :1093): four FMA chains over x[4i+j], then
+// 0 + l0 + l1 + l2 + l3.  xt is the TRANSPOSED fp32 vector in shared memory: xt[j * n/4 + i] = x[4i + j], so lane j
+// streams its chain with 16-byte loads, double-buffered (5.4 cycles per dependent step on B200, profiles/r01: 2x the
+// natural-layout version).  Called by warp 0; returns the value in all its lanes.
+__device__ __forceinline__ float sumsq_chain_t(const float* xt, int n, int lane) {
+    float acc = 0.0f;
+    if (lane < 4) {
+        const int nv = n >> 4;                                // float4s per chain
+        const float4* p = reinterpret_cast<const float4*>(xt + lane * (n >> 2));
+        constexpr int B = 8;
+        int i = 0;
+        if (nv >= B) {
+            float4 cur[B], nxt[B];
+#pragma unroll
+            for (int u = 0; u < B; ++u) cur[u] = p[u];
+#pragma unroll 1
+            for (; i + B <= nv; i += B) {
+#pragma unroll
+                for (int u = 0; u < B; ++u) nxt[u] = p[min(i + B + u, nv - 1)];
+#pragma unroll
+                for (int u = 0; u < B; ++u) {
+                    acc = __fmaf_rn(cur[u].x, cur[u].x, acc); acc = __fmaf_rn(cur[u].y, cur[u].y, acc);
+                    acc = __fmaf_rn(cur[u].z, cur[u].z, acc); acc = __fmaf_rn(cur[u].w, cur[u].w, acc);
+                }
+#pragma unroll
+                for (int u = 0; u < B; ++u) cur[u] = nxt[u];
+            }
+        }
+#pragma unroll 1
+        for (; i < nv; ++i) {
+            const float4 v = p[i];
+            acc = __fmaf_rn(v.x, v.x, acc); acc = __fmaf_rn(v.y, v.y, acc);
+            acc = __fmaf_rn(v.z, v.z, acc); acc = __fmaf_rn(v.w, v.w, acc);
+        }
+    }
+    const float l0 = __shfl_sync(kFull, acc, 0), l1 = __shfl_sync(kFull, acc, 1);
+    const float l2 = __shfl_sync(kFull, acc, 2), l3 = __shfl_sync(kFull, acc, 3);
+    float res = __fadd_rn(0.0f, l0);
+    res = __fadd_rn(res, l1);
+    res = __fadd_rn(res, l2);
+    res = __fadd_rn(res, l3);
+    return res;
+}
+
+// Rebuild the quantised activation vector of a phase in shared memory (every CTA, redundantly) from the tagged vector
+// `src`, waiting for every word to carry `tag`.
 //   gain != NULL: y = (x*w)*r, r = 1/sqrt(mean(x^2)+eps) (simd::rmsnorm, x86_simd.cpp:1754);  gain == NULL: y = x.
+// Thread layout: 8 lanes per quantisation group, 32 groups per pass, MAXP passes per batch; all loads of a batch are in
+// flight before the first tag is looked at.  The rmsnorm case needs the whole vector before its scale is known, so it
+// must fit ONE batch (K <= 24 * 256 = 6144, checked by the host): the products x*w and the group maxima wait in
+// registers while warp 0 walks the sum-of-squares chain (max |(x*w)*r| == (max |x*w|)*r: rounding is monotonic, r > 0).
 template <int QT, int GS>
-__device__ __forceinline__ void build_activation(uint8_t* xq, float* xs, float* xf, float* misc, const float* in, const float* gain,
-                                                 int K, int nkb, float* tap, int tid, Prof& pf) {
+__device__ __forceinline__ void build_activation(uint8_t* xq, float* xs, float* xt, float* misc, const uint2* src, uint32_t tag,
+                                                 const float* gain, int K, int nkb, float* tap, int tid, Prof& pf) {
     using T = Traits<QT, GS>;
     constexpr int PER = GS / 8;                 // values per thread per group
+    constexpr int LPP = PER / 2;                // 16-byte loads per thread per pass
     constexpr int GPP = kConsumerThreads / 8;   // groups per pass
+    constexpr int MAXP = 24 / PER;              // passes per batch (24 values per thread: registers, not shared memory)
     const int warp = tid >> 5, lane = tid & 31;
     const int kpad = nkb * kKBlockElems;
     const int G = K / GS;
     const int sub = tid & 7, g0 = tid >> 3;
-    // zero the padded tail so padded groups contribute fma(0, 0, acc) == acc
-    for (int i = K * T::ES + tid * 4; i < kpad * T::ES; i += kConsumerThreads * 4) *reinterpret_cast<uint32_t*>(xq + i) = 0u;
-    for (int i = G + tid; i < nkb * 8 * T::GPL; i += kConsumerThreads) xs[i] = 0.0f;
     const int n_pass = ceil_div(G, GPP);
-    float rr = 1.0f;
-    if (gain) {
 #pragma unroll 1
-        for (int i = tid; i < K / 4; i += kConsumerThreads)
-            reinterpret_cast<float4*>(xf)[i] = __ldcg(reinterpret_cast<const float4*>(in) + i);
-        consumer_sync();
-        pf.stop(tid, 8);
-        if (warp == 0) {
-            const float ss = sumsq_chain_warp0(xf, K, lane);
-            if (lane == 0) misc[0] = rms_scale(ss, K);
-        }
-        consumer_sync();
-        pf.stop(tid, 9);
-        rr = misc[0];
-    }
-    // software-pipelined over passes: the next pass's operands are in flight while this pass is divided and stored
-    float4 nx[PER / 4], nw[PER / 4];
+    for (int b0 = 0; b0 < n_pass; b0 += MAXP) {
+        uint4 w[MAXP][LPP];
+        float4 gw[MAXP][PER / 4];
 #pragma unroll
-    for (int q = 0; q < PER / 4; ++q) { nx[q] = make_float4(0.f, 0.f, 0.f, 0.f); nw[q] = nx[q]; }
-    auto fetch = [&](int ps) {
-        const int g = g0 + ps * GPP;
-        if (ps < n_pass && g < G) {
+        for (int ps = 0; ps < MAXP; ++ps) {
+            const int g = g0 + (b0 + ps) * GPP;
+            if (b0 + ps < n_pass && g < G) {
+                const uint2* s = src + g * GS + sub * PER;
 #pragma unroll
-            for (int q = 0; q < PER / 4; ++q) {
+                for (int q = 0; q < LPP; ++q) w[ps][q] = ld_tag2(s + 2 * q);
                 if (gain) {
-                    nx[q] = reinterpret_cast<const float4*>(xf + g * GS + sub * PER)[q];
-                    nw[q] = __ldg(reinterpret_cast<const float4*>(gain + g * GS + sub * PER) + q);
-                } else {
-                    nx[q] = __ldcg(reinterpret_cast<const float4*>(in + g * GS + sub * PER) + q);
+#pragma unroll
+                    for (int q = 0; q < PER / 4; ++q) gw[ps][q] = __ldg(reinterpret_cast<const float4*>(gain + g * GS + sub * PER) + q);
                 }
             }
         }
-    };
-    fetch(0);
-#pragma unroll 1
-    for (int ps = 0; ps < n_pass; ++ps) {
-        const int g = g0 + ps * GPP;
-        float y[PER];
+        bool again;
+        do {
+            again = false;
 #pragma unroll
-        for (int q = 0; q < PER / 4; ++q) {
-            if (gain) {     // (x*w)*r, multiply_avx256 x86_simd.cpp:1359
-                y[4 * q] = __fmul_rn(__fmul_rn(nx[q].x, nw[q].x), rr); y[4 * q + 1] = __fmul_rn(__fmul_rn(nx[q].y, nw[q].y), rr);
-                y[4 * q + 2] = __fmul_rn(__fmul_rn(nx[q].z, nw[q].z), rr); y[4 * q + 3] = __fmul_rn(__fmul_rn(nx[q].w, nw[q].w), rr);
-            } else {
-                y[4 * q] = nx[q].x; y[4 * q + 1] = nx[q].y; y[4 * q + 2] = nx[q].z; y[4 * q + 3] = nx[q].w;
+            for (int ps = 0; ps < MAXP; ++ps) {
+                const int g = g0 + (b0 + ps) * GPP;
+                if (b0 + ps < n_pass && g < G) {
+                    const uint2* s = src + g * GS + sub * PER;
+#pragma unroll
+                    for (int q = 0; q < LPP; ++q)
+                        if (w[ps][q].y != tag || w[ps][q].w != tag) { w[ps][q] = ld_tag2(s + 2 * q); again = true; }
+                }
+            }
+        } while (again);
+        pf.stop(tid, 0);
+        if (b0 + MAXP >= n_pass) pf.mark(tid, pf.trace_slot, pf.trace_slot >= 0);
+        if (b0 == 0) {
+            // every warp has left the previous phase (its drain / attention read the image this build overwrites)
+            consumer_sync();
+            // zero the padded tail so padded groups contribute fma(0, 0, acc) == acc
+            for (int i = K * T::ES + tid * 4; i < kpad * T::ES; i += kConsumerThreads * 4) *reinterpret_cast<uint32_t*>(xq + i) = 0u;
+            for (int i = G + tid; i < nkb * 8 * T::GPL; i += kConsumerThreads) xs[i] = 0.0f;
+        }
+        float y[MAXP][PER];
+        float m[MAXP];
+#pragma unroll
+        for (int ps = 0; ps < MAXP; ++ps) {
+#pragma unroll
+            for (int q = 0; q < LPP; ++q) { y[ps][2 * q] = __uint_as_float(w[ps][q].x); y[ps][2 * q + 1] = __uint_as_float(w[ps][q].z); }
+        }
+        float rr = 1.0f;
+        if (gain) {
+            // raw x -> transposed image for the chain; products and group maxima stay in registers
+#pragma unroll
+            for (int ps = 0; ps < MAXP; ++ps) {
+                const int g = g0 + (b0 + ps) * GPP;
+                if (b0 + ps < n_pass && g < G) {
+                    const int e0 = g * GS + sub * PER;                   // multiple of 4
+                    if (PER == 8) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) *reinterpret_cast<float2*>(xt + j * (K >> 2) + (e0 >> 2)) = make_float2(y[ps][j], y[ps][(4 + j) % PER]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) xt[j * (K >> 2) + (e0 >> 2)] = y[ps][j];
+                    }
+#pragma unroll
+                    for (int q = 0; q < PER / 4; ++q) {                 // x*w, multiply_avx256 x86_simd.cpp:1359
+                        y[ps][4 * q] = __fmul_rn(y[ps][4 * q], gw[ps][q].x); y[ps][4 * q + 1] = __fmul_rn(y[ps][4 * q + 1], gw[ps][q].y);
+                        y[ps][4 * q + 2] = __fmul_rn(y[ps][4 * q + 2], gw[ps][q].z); y[ps][4 * q + 3] = __fmul_rn(y[ps][4 * q + 3], gw[ps][q].w);
+                    }
+                }
             }
         }
-        fetch(ps + 1);
-        float m = 0.0f;
 #pragma unroll
-        for (int i = 0; i < PER; ++i) m = fmaxf(m, fabsf(y[i]));
-        m = group_max8(m);
-        if (g < G) quant_store<QT, GS>(xq, xs, y, m, g, sub, tap);
+        for (int ps = 0; ps < MAXP; ++ps) {
+            const int g = g0 + (b0 + ps) * GPP;
+            float mm = 0.0f;
+            if (b0 + ps < n_pass && g < G) {
+#pragma unroll
+                for (int i = 0; i < PER; ++i) mm = fmaxf(mm, fabsf(y[ps][i]));
+            }
+            m[ps] = group_max8(mm);
+        }
+        if (gain) {
+            consumer_sync();
+            pf.stop(tid, 8);
+            if (warp == 0) {
+                const float ss = sumsq_chain_t(xt, K, lane);
+                if (lane == 0) misc[0] = rms_scale(ss, K);
+            }
+            consumer_sync();
+            pf.stop(tid, 9);
+            rr = misc[0];
+        }
+#pragma unroll
+        for (int ps = 0; ps < MAXP; ++ps) {
+            const int g = g0 + (b0 + ps) * GPP;
+            if (b0 + ps < n_pass && g < G) {
+                if (gain) {
+#pragma unroll
+                    for (int i = 0; i < PER; ++i) y[ps][i] = __fmul_rn(y[ps][i], rr);     // (x*w)*r
+                    m[ps] = __fmul_rn(m[ps], rr);
+                }
+                quant_store<QT, GS>(xq, xs, y[ps], m[ps], g, sub, tap);
+            }
+        }
     }
     consumer_sync();
 }
@@ -329,10 +451,17 @@ __device__ __forceinline__ float stage_chain(const uint8_t* sp, int nu, const ui
 
 // ---------------------------------------------------------------------------------------------- attention part
 // execute_attn (transformer.cpp:397-455) for query head qh, CTA `part` of `cph`: scores for a contiguous share of
-// the keys, score exchange through L2, full softmax (redundantly per part), PV chains for HS/cph head dims.
+// the keys, score exchange through L2 (tagged words), full softmax (redundantly per part), PV chains for HS/cph head dims.
+//
+// Everything that does not depend on the new token is requested BEFORE the q/k/v rows are polled: the part's K rows
+// (registers), its V column block (TMA bulk copies into a ring of 4 KB chunks, the V cache is stored in column blocks of
+// HS/cph for exactly this) and the RoPE table row.  The two serial sections - softmax's sum and the PV chains - run
+// as register-double-buffered FP32 chains at ~5.5 cycles per dependent step.
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 template <int HS>
-__device__ __forceinline__ void attention_part(const MegaParams& p, uint8_t* smem, int layer, int qh, int part,
-                                               unsigned long long head_target, int tid, Prof& pf) {
+__device__ __forceinline__ void attention_part(const MegaParams& p, uint8_t* smem, int layer, int qh, int part, int pos, int bs,
+                                               uint32_t tag_qkv, uint32_t tag_score, uint32_t tag_out, int tid, Prof& pf) {
     constexpr int EPL = HS / 8;
     const int cph = p.cph;
     const int DW = HS / cph;                                // head dims owned by this part
@@ -341,107 +470,115 @@ __device__ __forceinline__ void attention_part(const MegaParams& p, uint8_t* sme
     float* k_s = q_s + HS;
     float* v_s = k_s + HS;
     float* red = reinterpret_cast<float*>(smem + p.off_misc);
+    uint32_t* vcount = reinterpret_cast<uint32_t*>(smem + p.off_misc) + 28;      // V chunks streamed so far by this CTA (ring position)
     float* v_stage = reinterpret_cast<float*>(smem + p.off_vstage);
-    const int VR = p.v_chunk_rows;
+    uint64_t* vfull = reinterpret_cast<uint64_t*>(smem + p.off_vbars);
+    const int VR = p.v_chunk_rows, NCH = p.n_vchunks;
 
     const int hgs = p.n_heads / p.n_kv_heads;
     const int kvh = qh / hgs, g = qh % hgs;
     const int dim = p.n_heads * HS, kv_dim = p.n_kv_heads * HS;
-    const int pos = __ldcg(&p.st->pos), bs = __ldcg(&p.st->bs);     // state changes between steps of one launch: bypass L1
     const int n = pos + 1;
     const int warp = tid >> 5, lane = tid & 31;
     const size_t cache_off = ((size_t)layer * p.n_kv_heads + kvh) * p.max_seq * HS;
     float* kc = p.k_cache + cache_off;
-    float* vc = p.v_cache + cache_off;
+    float* vc = p.v_cache + cache_off + (size_t)part * p.max_seq * DW;      // this part's column block: [max_seq][DW]
     const int d0 = part * DW;
 
-    // V stream for this part's dims: rows [0, pos) from the cache in chunks of VR rows, 3 chunks in flight
-    const int n_chunks = ceil_div(n, VR);
-    const int ppr = DW / 4;                                 // 16-byte pieces per row
-    auto issue_v_chunk = [&](int ch) {
-        if (ch < n_chunks) {
-            const int t0 = ch * VR;
-            float* dst = v_stage + (size_t)(ch % 3) * VR * DW;
-            const int rows = min(VR, pos - t0);
-            for (int i = tid; i < rows * ppr; i += kConsumerThreads) {
-                const int row = i / ppr, pc = i - row * ppr;
-                cp_async16(dst + (size_t)row * DW + pc * 4, vc + (size_t)(t0 + row) * HS + d0 + pc * 4);
+    // ---- V ring: chunk c = cached rows [c*VR, min(pos, (c+1)*VR)) of the column block, one bulk copy each
+    const int n_chunks = ceil_div(pos, VR);                 // the new row (t == pos) comes from v_s
+    const uint32_t vbase = *vcount;
+    auto issue_v = [&](int c) {                             // one thread
+        const uint32_t gidx = vbase + (uint32_t)c;
+        const uint32_t slot = gidx % (uint32_t)NCH;
+        const uint32_t bytes = (uint32_t)min(VR, pos - c * VR) * DW * 4;
+        mbar_arrive_expect_tx(&vfull[slot], bytes);
+        bulk_g2s(v_stage + (size_t)slot * VR * DW, vc + (size_t)c * VR * DW, bytes, &vfull[slot]);
+    };
+    if (tid == 0) {
+        fence_proxy_async();                                // the ring aliases memory the generic proxy wrote (activation image)
+        for (int c = 0; c < min(NCH, n_chunks); ++c) issue_v(c);
+    }
+
+    // ---- this part's keys; the first batches of K rows are requested before the q/k/v rows are polled
+    const int per = ceil_div(ceil_div(n, cph), 4) * 4;
+    const int tb = part * per, te = min(n, tb + per);
+    const int rr = lane >> 3, j = lane & 7;
+    constexpr int UU = 3;
+    float4 kv[UU][EPL / 4];
+    auto load_k = [&](int base) {
+#pragma unroll
+        for (int u = 0; u < UU; ++u) {
+            const int t = base + (u * kConsumerWarps + warp) * 4 + rr;
+            if (t < pos && t < te) {
+                const float4* kp = reinterpret_cast<const float4*>(kc + (size_t)t * HS + j * EPL);
+#pragma unroll
+                for (int q = 0; q < EPL / 4; ++q) kv[u][q] = __ldcg(kp + q);
+            } else {
+#pragma unroll
+                for (int q = 0; q < EPL / 4; ++q) kv[u][q] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
-        cp_async_commit();
     };
-    issue_v_chunk(0); issue_v_chunk(1); issue_v_chunk(2);
+    load_k(tb);
 
+    // ---- q, k, v rows of this head: 3 * HS tagged words, one 16-byte load (= one RoPE pair) per thread
     // RoPE + KV append (rope_v2 tf_operators.cpp:355-402; transformer.cpp:431-439)
-    const float* qkv = p.qkv;
-    if (tid < HS / 2) {
+    if (tid < 3 * (HS / 2)) {
+        const int sect = tid / (HS / 2), i = tid - sect * (HS / 2);
         // sequence_rope_v2 (tensor.h:262-270) walks all bs*hgs rows of the q tensor with position pos0 + row: query head g
         // of a GQA group is rotated at pos + g*bs (== pos when n_heads == n_kv_heads).  Reproduced, not fixed.
-        const float2 cs2 = __ldg(reinterpret_cast<const float2*>(p.rope) + (size_t)(pos + g * bs) * (HS / 2) + tid);
-        const float2 x = __ldcg(reinterpret_cast<const float2*>(qkv + (size_t)qh * HS) + tid);
-        float o0, o1;
-        rope_pair(cs2.x, cs2.y, x.x, x.y, o0, o1);
-        q_s[2 * tid] = o0; q_s[2 * tid + 1] = o1;
-    } else if (tid < HS) {
-        const int i = tid - HS / 2;
-        const float2 cs2 = __ldg(reinterpret_cast<const float2*>(p.rope) + (size_t)pos * (HS / 2) + i);
-        const float2 x = __ldcg(reinterpret_cast<const float2*>(qkv + dim + (size_t)kvh * HS) + i);
-        float o0, o1;
-        rope_pair(cs2.x, cs2.y, x.x, x.y, o0, o1);
-        k_s[2 * i] = o0; k_s[2 * i + 1] = o1;
-        if (g == 0 && part == 0) {
-            float* krow = kc + (size_t)pos * HS;
-            krow[((2 * i) & 7) * EPL + ((2 * i) >> 3)] = o0;
-            krow[((2 * i + 1) & 7) * EPL + ((2 * i + 1) >> 3)] = o1;
+        const float2 cs2 = __ldg(reinterpret_cast<const float2*>(p.rope) + (size_t)(sect == 0 ? pos + g * bs : pos) * (HS / 2) + i);
+        const uint2* src = p.qkvt + (sect == 0 ? (size_t)qh * HS : sect == 1 ? (size_t)dim + (size_t)kvh * HS : (size_t)dim + kv_dim + (size_t)kvh * HS) + 2 * i;
+        uint4 w = ld_tag2(src);
+        while (w.y != tag_qkv || w.w != tag_qkv) w = ld_tag2(src);
+        const float x0 = __uint_as_float(w.x), x1 = __uint_as_float(w.z);
+        if (sect == 0) {
+            float o0, o1;
+            rope_pair(cs2.x, cs2.y, x0, x1, o0, o1);
+            q_s[2 * i] = o0; q_s[2 * i + 1] = o1;
+        } else if (sect == 1) {
+            float o0, o1;
+            rope_pair(cs2.x, cs2.y, x0, x1, o0, o1);
+            k_s[2 * i] = o0; k_s[2 * i + 1] = o1;
+            if (g == 0 && part == 0) {
+                float* krow = kc + (size_t)pos * HS;
+                krow[((2 * i) & 7) * EPL + ((2 * i) >> 3)] = o0;
+                krow[((2 * i + 1) & 7) * EPL + ((2 * i + 1) >> 3)] = o1;
+            }
+        } else {
+            v_s[2 * i] = x0; v_s[2 * i + 1] = x1;
+            if (g == 0 && part == 0) {
+                float* vrow = p.v_cache + cache_off + ((size_t)((2 * i) / DW) * p.max_seq + pos) * DW + (2 * i) % DW;
+                *reinterpret_cast<float2*>(vrow) = make_float2(x0, x1);
+            }
         }
-    } else if (tid < HS + HS / 4) {
-        const int i = tid - HS;
-        const float4 v = __ldcg(reinterpret_cast<const float4*>(qkv + dim + kv_dim + (size_t)kvh * HS) + i);
-        reinterpret_cast<float4*>(v_s)[i] = v;
-        if (g == 0 && part == 0) reinterpret_cast<float4*>(vc + (size_t)pos * HS)[i] = v;
     }
     consumer_sync();
     pf.stop(tid, 10);
+    pf.mark(tid, 28, pf.trace_slot >= 0);
 
-    // scores for this part's keys: float dot_product_avx256 (x86_simd.cpp:1447-1468): 8 FMA chains, then 0 + l0 + ... + l7
-    const int per = ceil_div(ceil_div(n, cph), 4) * 4;
-    const int tb = part * per, te = min(n, tb + per);
-    float* att_g = p.att_scratch + (size_t)qh * p.max_seq;
+    // ---- scores for this part's keys: float dot_product_avx256 (x86_simd.cpp:1447-1468): 8 FMA chains, then 0 + l0 + ... + l7
+    uint2* att_g = p.score_t + (size_t)qh * p.score_stride;
     {
-        const int rr = lane >> 3, j = lane & 7;
-        float qr[EPL];
-#pragma unroll
-        for (int i = 0; i < EPL; ++i) qr[i] = q_s[8 * i + j];
-        constexpr int UU = 2;
+        const float* qj = q_s + j;                 // q values of this AVX lane are re-read from shared memory (registers are scarce)
 #pragma unroll 1
         for (int base = tb; base < te; base += kConsumerWarps * 4 * UU) {
-            float4 kv[UU][EPL / 4];
-#pragma unroll
-            for (int u = 0; u < UU; ++u) {
-                const int t = base + (u * kConsumerWarps + warp) * 4 + rr;
-                if (t < pos && t < te) {
-                    const float4* kp = reinterpret_cast<const float4*>(kc + (size_t)t * HS + j * EPL);
-#pragma unroll
-                    for (int q = 0; q < EPL / 4; ++q) kv[u][q] = __ldcg(kp + q);
-                } else if (t == pos && t < te) {
-#pragma unroll
-                    for (int q = 0; q < EPL / 4; ++q)
-                        kv[u][q] = make_float4(k_s[8 * (4 * q) + j], k_s[8 * (4 * q + 1) + j], k_s[8 * (4 * q + 2) + j], k_s[8 * (4 * q + 3) + j]);
-                } else {
-#pragma unroll
-                    for (int q = 0; q < EPL / 4; ++q) kv[u][q] = make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-            }
 #pragma unroll
             for (int u = 0; u < UU; ++u) {
                 const int t = base + (u * kConsumerWarps + warp) * 4 + rr;
                 float acc = 0.0f;
+                if (t == pos) {
+#pragma unroll
+                    for (int q = 0; q < EPL / 4; ++q)
+                        kv[u][q] = make_float4(k_s[8 * (4 * q) + j], k_s[8 * (4 * q + 1) + j], k_s[8 * (4 * q + 2) + j], k_s[8 * (4 * q + 3) + j]);
+                }
 #pragma unroll
                 for (int q = 0; q < EPL / 4; ++q) {
-                    acc = __fmaf_rn(kv[u][q].x, qr[4 * q], acc);
-                    acc = __fmaf_rn(kv[u][q].y, qr[4 * q + 1], acc);
-                    acc = __fmaf_rn(kv[u][q].z, qr[4 * q + 2], acc);
-                    acc = __fmaf_rn(kv[u][q].w, qr[4 * q + 3], acc);
+                    acc = __fmaf_rn(kv[u][q].x, qj[8 * (4 * q)], acc);
+                    acc = __fmaf_rn(kv[u][q].y, qj[8 * (4 * q + 1)], acc);
+                    acc = __fmaf_rn(kv[u][q].z, qj[8 * (4 * q + 2)], acc);
+                    acc = __fmaf_rn(kv[u][q].w, qj[8 * (4 * q + 3)], acc);
                 }
                 float tot = 0.0f;
 #pragma unroll
@@ -449,27 +586,30 @@ __device__ __forceinline__ void attention_part(const MegaParams& p, uint8_t* sme
                 if (j == 0 && t < te) {
                     const float sc = __fmul_rn(tot, p.attn_scale);      // att.multiply(attn_scale), transformer.cpp:443
                     att[t] = sc;
-                    if (cph > 1) att_g[t] = sc;
+                    if (cph > 1) st_tag(att_g + t, sc, tag_score);
                 }
+            }
+            if (base + kConsumerWarps * 4 * UU < te) load_k(base + kConsumerWarps * 4 * UU);     // contexts beyond 96 * cph keys: one more round trip per batch
+        }
+    }
+    pf.stop(tid, 11);
+    // ---- exchange: fetch the other parts' scores (two tagged words per load), waiting for their tag
+    if (cph > 1) {
+#pragma unroll 1
+        for (int t = 2 * tid; t < n; t += 2 * kConsumerThreads) {
+            const bool need0 = (t < tb || t >= te), need1 = (t + 1 < n) && (t + 1 < tb || t + 1 >= te);
+            if (need0 || need1) {
+                uint4 w = ld_tag2(att_g + t);
+                while ((need0 && w.y != tag_score) || (need1 && w.w != tag_score)) w = ld_tag2(att_g + t);
+                if (need0) att[t] = __uint_as_float(w.x);
+                if (need1) att[t + 1] = __uint_as_float(w.z);
             }
         }
     }
-    // exchange: wait until all parts of this head have published their scores, then fetch the others'
     consumer_sync();
-    pf.stop(tid, 11);
-    if (cph > 1) {
-        if (tid == 0) {
-            red_release_add_u64(p.head_ctr + qh, 1ull);
-            while (ld_acquire_u64(p.head_ctr + qh) < head_target) { }
-        }
-        consumer_sync();
-        for (int t = tid; t < n; t += kConsumerThreads)
-            if (t < tb || t >= te) att[t] = __ldcg(att_g + t);
-        consumer_sync();
-    }
     pf.stop(tid, 12);
 
-    // softmax_sisd (tf_operators.cpp:176-186): max, expf(x - max), serial sum, divide
+    // ---- softmax_sisd (tf_operators.cpp:176-186): max, expf(x - max), serial sum, divide
     float m = -INFINITY;
     for (int t = tid; t < n; t += kConsumerThreads) m = fmaxf(m, att[t]);
 #pragma unroll
@@ -480,19 +620,23 @@ __device__ __forceinline__ void attention_part(const MegaParams& p, uint8_t* sme
 #pragma unroll
     for (int w = 1; w < kConsumerWarps; ++w) m = fmaxf(m, red[w]);
     for (int t = tid; t < n; t += kConsumerThreads) att[t] = expf_exact(__fsub_rn(att[t], m));
+    if (tid < 8) att[n + tid] = 0.0f;                      // the chains below read whole float4s
     consumer_sync();
     if (tid == 0) {
+        // one FP32 add chain in index order; loads run one batch ahead of the adds
+        const float4* a4 = reinterpret_cast<const float4*>(att);
+        const int nv = n >> 2;
         float sum = 0.0f;
-        int t = 0;
+        float4 c0 = a4[0], c1 = a4[1];
+        int i = 0;
 #pragma unroll 1
-        for (; t + 8 <= n; t += 8) {
-            float e[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) e[u] = att[t + u];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) sum = __fadd_rn(sum, e[u]);
+        for (; i + 2 <= nv; i += 2) {
+            const float4 n0 = a4[i + 2], n1 = a4[i + 3];
+            sum = __fadd_rn(sum, c0.x); sum = __fadd_rn(sum, c0.y); sum = __fadd_rn(sum, c0.z); sum = __fadd_rn(sum, c0.w);
+            sum = __fadd_rn(sum, c1.x); sum = __fadd_rn(sum, c1.y); sum = __fadd_rn(sum, c1.z); sum = __fadd_rn(sum, c1.w);
+            c0 = n0; c1 = n1;
         }
-        for (; t < n; ++t) sum = __fadd_rn(sum, att[t]);
+        for (int t = 4 * i; t < n; ++t) sum = __fadd_rn(sum, att[t]);
         red[16] = sum;
     }
     consumer_sync();
@@ -501,46 +645,66 @@ __device__ __forceinline__ void attention_part(const MegaParams& p, uint8_t* sme
     consumer_sync();
     pf.stop(tid, 13);
 
-    // weighted_sum (tf_operators.cpp:325-350): o = V[0]*w0; t >= 1: if |w_t| > 1e-15: o = fma(V[t], w_t, o) — one chain
-    // per head dim, branch-free (a skipped row keeps o through a select)
-    float o = 0.0f;
+    // ---- weighted_sum (tf_operators.cpp:325-350): o = V[0]*w0; t >= 1: if |w_t| > 1e-15: o = fma(V[t], w_t, o) — one chain
+    // per head dim, run by the first DW threads without CTA-wide synchronisation; thread 0 refills the chunk ring.
+    if (tid < DW) {
+        float o = 0.0f;
+        bool first = true;
 #pragma unroll 1
-    for (int ch = 0; ch < n_chunks; ++ch) {
-        cp_async_wait<2>();
-        consumer_sync();
-        pf.stop(tid, 14);
-        if (tid < DW) {
-            float* vb = v_stage + (size_t)(ch % 3) * VR * DW;
-            const int t0 = ch * VR, t1 = min(n, t0 + VR);
-            if (pos >= t0 && pos < t1) vb[(size_t)(pos - t0) * DW + tid] = v_s[d0 + tid];   // the new row joins its chunk
-            int t = t0;
-            if (t == 0) { o = __fmul_rn(vb[tid], att[0]); t = 1; }
-            constexpr int PB = 8;
+        for (int c = 0; c < n_chunks; ++c) {
+            const uint32_t gidx = vbase + (uint32_t)c;
+            const uint32_t slot = gidx % (uint32_t)NCH;
+            mbar_wait(&vfull[slot], (gidx / (uint32_t)NCH) & 1u);
+            const float* vb = v_stage + (size_t)slot * VR * DW + tid;
+            const int t0 = c * VR, rows = min(VR, pos - t0);
+            const float* wp = att + t0;
+            int i = 0;
+            if (first) { o = __fmul_rn(vb[0], wp[0]); i = 1; first = false; }
+            // head of the chunk up to a multiple of 4 rows, then 8 rows per iteration with the loads one iteration ahead
+            for (; i < rows && (i & 3); ++i) { const float w = wp[i]; if (fabsf(w) > 1e-15f) o = __fmaf_rn(vb[(size_t)i * DW], w, o); }
+            if (i + 8 <= rows) {
+                float4 w0 = *reinterpret_cast<const float4*>(wp + i), w1 = *reinterpret_cast<const float4*>(wp + i + 4);
+                float v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = vb[(size_t)(i + u) * DW];
 #pragma unroll 1
-            for (; t + PB <= t1; t += PB) {
-                float vv[PB], ww[PB];
+                for (; i + 8 <= rows; i += 8) {
+                    float4 nw0 = w0, nw1 = w1;
+                    float nv[8];
+                    const bool more = i + 16 <= rows;
+                    if (more) { nw0 = *reinterpret_cast<const float4*>(wp + i + 8); nw1 = *reinterpret_cast<const float4*>(wp + i + 12); }
 #pragma unroll
-                for (int u = 0; u < PB; ++u) { ww[u] = att[t + u]; vv[u] = vb[(size_t)(t + u - t0) * DW + tid]; }
+                    for (int u = 0; u < 8; ++u) nv[u] = more ? vb[(size_t)(i + 8 + u) * DW] : 0.0f;
+                    if (fabsf(w0.x) > 1e-15f) o = __fmaf_rn(v[0], w0.x, o);
+                    if (fabsf(w0.y) > 1e-15f) o = __fmaf_rn(v[1], w0.y, o);
+                    if (fabsf(w0.z) > 1e-15f) o = __fmaf_rn(v[2], w0.z, o);
+                    if (fabsf(w0.w) > 1e-15f) o = __fmaf_rn(v[3], w0.w, o);
+                    if (fabsf(w1.x) > 1e-15f) o = __fmaf_rn(v[4], w1.x, o);
+                    if (fabsf(w1.y) > 1e-15f) o = __fmaf_rn(v[5], w1.y, o);
+                    if (fabsf(w1.z) > 1e-15f) o = __fmaf_rn(v[6], w1.z, o);
+                    if (fabsf(w1.w) > 1e-15f) o = __fmaf_rn(v[7], w1.w, o);
+                    w0 = nw0; w1 = nw1;
 #pragma unroll
-                for (int u = 0; u < PB; ++u) {
-                    const float nf = __fmaf_rn(vv[u], ww[u], o);
-                    o = (fabsf(ww[u]) > 1e-15f) ? nf : o;
+                    for (int u = 0; u < 8; ++u) v[u] = nv[u];
                 }
             }
-            for (; t < t1; ++t) {
-                const float w = att[t];
-                const float nf = __fmaf_rn(vb[(size_t)(t - t0) * DW + tid], w, o);
-                o = (fabsf(w) > 1e-15f) ? nf : o;
-            }
+            for (; i < rows; ++i) { const float w = wp[i]; if (fabsf(w) > 1e-15f) o = __fmaf_rn(vb[(size_t)i * DW], w, o); }
+            // the chunk is consumed: refill its slot with chunk c + NCH
+            if (DW > 32) asm volatile("bar.sync 2, %0;" :: "r"(DW) : "memory"); else __syncwarp(DW == 32 ? kFull : ((1u << DW) - 1u));
+            if (tid == 0 && c + NCH < n_chunks) { fence_proxy_async(); issue_v(c + NCH); }
         }
-        consumer_sync();
-        pf.stop(tid, 15);
-        issue_v_chunk(ch + 3);
-        pf.stop(tid, 16);
+        {   // the new token's row
+            const float w = att[pos], v = v_s[d0 + tid];
+            if (first) o = __fmul_rn(v, w);
+            else if (fabsf(w) > 1e-15f) o = __fmaf_rn(v, w, o);
+        }
+        st_tag(p.attnt + (size_t)qh * HS + d0 + tid, o, tag_out);
+        if (tid == 0) {
+            *vcount = vbase + (uint32_t)n_chunks;
+            if (pf.p && pf.trace_slot >= 0) pf.p[29] = gtimer();
+        }
     }
-    cp_async_wait<0>();
-    if (tid < DW) p.attn[(size_t)qh * HS + d0 + tid] = o;
-    pf.stop(tid, 17);
+    pf.stop(tid, 15);
 }
 
 // ---------------------------------------------------------------------------------------------- the kernel
@@ -548,15 +712,20 @@ template <int QT, int GS, int HS>
 __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __grid_constant__ MegaParams p) {
     using T = Traits<QT, GS>;
     using R = Ring<QT, GS>;
-    extern __shared__ __align__(128) uint8_t smem[];
+    extern __shared__ __align__(16) uint8_t smem[];
     uint8_t* ring = smem + p.off_ring;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.off_bars);
     uint64_t* empty = full + p.n_slots;
+    uint32_t* issued = reinterpret_cast<uint32_t*>(smem + p.off_misc) + 30;      // stages issued so far (producer -> consumers)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n_slots = p.n_slots;
 
     if (tid == 0) {
         for (int i = 0; i < n_slots; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        uint64_t* vfull = reinterpret_cast<uint64_t*>(smem + p.off_vbars);
+        for (int i = 0; i < p.n_vchunks; ++i) mbar_init(&vfull[i], 1);
+        *issued = 0u;
+        reinterpret_cast<uint32_t*>(smem + p.off_misc)[28] = 0u;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -566,7 +735,13 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
     if (warp == kConsumerWarps) {
         // ================= TMA producer =================
         if (lane == 0) {
-            uint32_t sc = 0;
+            uint32_t sc = 0, slot = 0, par = 1;         // empty[] parity to wait for: 1 passes on a fresh barrier
+            // In-flight window: stage i is issued only after stage i - window has LANDED.  The ring is deep so that it can
+            // buffer microseconds of weights, but requests queued in the memory system are pure latency for everyone else
+            // (Little's law: 148 SMs x 180 KB outstanding = 4 us at HBM speed) - and "everyone else" is the tagged-word
+            // exchange every phase waits for.  ~40 KB in flight per SM already saturates HBM.
+            uint32_t wslot = 0, wpar = 0;
+            const uint32_t window = (uint32_t)p.window;
 #pragma unroll 1
             for (int step = 0; step < p.n_steps; ++step) {
 #pragma unroll 1
@@ -574,25 +749,34 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
                     const PhaseShape ph = phase_shape(p, pi);
                     const int t0 = (int)((long long)ph.n_tasks * blockIdx.x / gridDim.x);
                     const int t1 = (int)((long long)ph.n_tasks * (blockIdx.x + 1) / gridDim.x);
-                    const int spt_tile = ceil_div(ph.nkb, R::U), spt = ph.tt * spt_tile;
+                    const int spt_tile = ceil_div(ph.nkb, R::U);
+                    const uint32_t task_bytes = (uint32_t)ph.tt * ph.nkb * T::UNIT_BYTES;     // one warp's tile(s)
 #pragma unroll 1
                     for (int r0 = t0; r0 < t1; r0 += kConsumerWarps) {
                         const int nw = min(kConsumerWarps, t1 - r0);
+                        const uint8_t* round_base = ph.w + (size_t)r0 * task_bytes;
 #pragma unroll 1
-                        for (int s = 0; s < spt; ++s) {
-                            const int tile = s / spt_tile, ks = s - tile * spt_tile;
-                            const uint32_t bytes = (uint32_t)min(R::U, ph.nkb - ks * R::U) * T::UNIT_BYTES;
+                        for (int tile = 0; tile < ph.tt; ++tile) {
 #pragma unroll 1
-                            for (int w = 0; w < nw; ++w) {
-                                const uint32_t idx = sc + (uint32_t)(s * nw + w);
-                                const uint32_t slot = idx % (uint32_t)n_slots, k = idx / (uint32_t)n_slots;
-                                mbar_wait_sleep(&empty[slot], (k & 1u) ^ 1u);
-                                mbar_arrive_expect_tx(&full[slot], bytes);
-                                const uint8_t* src = ph.w + (((size_t)(r0 + w) * ph.tt + tile) * ph.nkb + (size_t)ks * R::U) * T::UNIT_BYTES;
-                                bulk_g2s(ring + (size_t)slot * R::SLOT_BYTES, src, bytes, &full[slot]);
+                            for (int ks = 0; ks < spt_tile; ++ks) {
+                                const uint32_t bytes = (uint32_t)min(R::U, ph.nkb - ks * R::U) * T::UNIT_BYTES;
+                                const uint8_t* src = round_base + ((size_t)tile * ph.nkb + (size_t)ks * R::U) * T::UNIT_BYTES;
+#pragma unroll 1
+                                for (int w = 0; w < nw; ++w) {
+                                    if (window < (uint32_t)n_slots && sc >= window) {
+                                        mbar_wait_sleep(&full[wslot], wpar);
+                                        if (++wslot == (uint32_t)n_slots) { wslot = 0; wpar ^= 1u; }
+                                    }
+                                    mbar_wait_sleep(&empty[slot], par);
+                                    mbar_arrive_expect_tx(&full[slot], bytes);
+                                    bulk_g2s(ring + (size_t)slot * R::SLOT_BYTES, src, bytes, &full[slot]);
+                                    __threadfence_block();                      // the barrier is armed before the count says so
+                                    st_shared_volatile_u32(issued, ++sc);
+                                    src += task_bytes;
+                                    if (++slot == (uint32_t)n_slots) { slot = 0; par ^= 1u; }
+                                }
                             }
                         }
-                        sc += (uint32_t)(nw * spt);
                     }
                 }
             }
@@ -603,51 +787,76 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
     // ================= consumers =================
     uint8_t* xq = smem + p.off_xq;
     float* xs = reinterpret_cast<float*>(smem + p.off_xs);
-    float* xf = reinterpret_cast<float*>(smem + p.off_xf);
+    float* xt = reinterpret_cast<float*>(smem + p.off_xt);
     float* misc = reinterpret_cast<float*>(smem + p.off_misc);
     float* cs = reinterpret_cast<float*>(smem + p.off_chain) + (size_t)warp * (R::U * 32 * 2 * T::GPL);
     const uint4* xq4 = reinterpret_cast<const uint4*>(xq);
     const int r = lane >> 3, l = lane & 7;
 
-    unsigned long long bar_target = __ldcg(p.bar_ctr + 1) + gridDim.x;
     const int n_attn_ctas = p.n_heads * p.cph;
     const bool attn_cta = (int)blockIdx.x < n_attn_ctas;
     const int my_head = blockIdx.x / p.cph, my_part = blockIdx.x % p.cph;
-    unsigned long long head_base = attn_cta ? __ldcg(p.head_ctr + p.n_heads + my_head) : 0ull;
-    unsigned long long attn_rounds = 0;
     uint32_t sc = 0;
     Prof pf;
     pf.p = p.prof ? p.prof + (size_t)blockIdx.x * 32 : nullptr;
     pf.t0 = pf.p ? gtimer() : 0ull;
+    pf.trace_slot = -1;
+
+    // sequence state at launch: written by the previous kernel on this stream.  Kept in shared memory, not registers:
+    // the phase loop below is register-bound (168 per thread with 9 warps on 4 schedulers) and must not spill.
+    int* sstate = reinterpret_cast<int*>(misc) + 26;          // [0] next token, [1] n_out
+    if (tid == 0) { sstate[0] = p.st->token; sstate[1] = p.st->n_out; }
+    const int pos0 = p.st->pos, bs0 = p.st->bs;
+    consumer_sync();
 
 #pragma unroll 1
     for (int step = 0; step < p.n_steps; ++step) {
-        const int token = __ldcg(&p.st->token);
-        const float* emb_row = p.emb + (size_t)token * p.dim;
-        float best_v = -INFINITY;
-        int best_i = 0x7fffffff;
+        const uint32_t tbase = p.epoch + 1u + (uint32_t)step * (uint32_t)(p.n_layers + 1) * kTagsPerLayer;   // tag(layer, k) = tbase + layer * 8 + k
+        const int pos = pos0 + step, bs = step == 0 ? bs0 : 1;
+        // embedding row (transformer.cpp:115-122): this CTA's slice of it becomes the input vector of layer 0
+        {
+            const int token = sstate[0];
+            const int e0 = (int)((long long)p.dim * blockIdx.x / gridDim.x), e1 = (int)((long long)p.dim * (blockIdx.x + 1) / gridDim.x);
+            for (int i = e0 + tid; i < e1; i += kConsumerThreads) st_tag(p.x1t + i, __ldg(p.emb + (size_t)token * p.dim + i), tbase);
+        }
+        pf.stop(tid, 19);
 #pragma unroll 1
         for (int pi = 0; pi < n_phases; ++pi) {
-            const PhaseShape ph = phase_shape(p, pi);
             const int layer = pi >> 2, pk = (pi == n_phases - 1) ? 4 : (pi & 3);
             const MegaLayer* L = p.layers + (pk == 4 ? 0 : layer);
-            // layer 0 reads the embedding row instead of x1 (transformer.cpp:115-122)
-            const float* x1_in = (layer == 0 && pk < 2) ? emb_row : p.x1;
-            // ---- producer side of the math: the activation vector of this phase
-            const float* in = (pk == 1) ? p.attn : (pk == 3) ? p.hd : x1_in;
+            const uint32_t tl = tbase + (uint32_t)layer * kTagsPerLayer;
+            // tags: +0 layer input (= +6 of the previous layer), +1 qkv, +2 scores, +3 attention out, +4 x1 after Wo, +5 hd, +6 x1 after W2
+            const uint32_t tag_x_in = (layer == 0) ? tbase : tl - kTagsPerLayer + 6u;
+            // ---- the activation vector of this phase
+            const uint2* in = (pk == 1) ? p.attnt : (pk == 3) ? p.hdt : p.x1t;
+            const uint32_t tag_in = (pk == 1) ? tl + 3u : (pk == 2) ? tl + 4u : (pk == 3) ? tl + 5u : tag_x_in;
             const float* gain = (pk == 0) ? L->att_norm : (pk == 2) ? L->ffn_norm : (pk == 4) ? p.out_norm : nullptr;
-            build_activation<QT, GS>(xq, xs, xf, misc, in, gain, ph.K, ph.nkb, (pk == 4 && blockIdx.x == 0) ? p.tap_norm : nullptr, tid, pf);
+            const bool traced = (step == p.n_steps - 1) && (layer == p.n_layers / 2) && pk < 4;
+            pf.trace_slot = traced ? 20 + pk : -1;
+            {
+                const int K = (pk == 3) ? p.hidden : p.dim;
+                build_activation<QT, GS>(xq, xs, xt, misc, in, tag_in, gain, K, ceil_div(K, kKBlockElems), (pk == 4 && blockIdx.x == 0) ? p.tap_norm : nullptr, tid, pf);
+            }
             pf.stop(tid, 1);
+            const PhaseShape ph = phase_shape(p, pi);        // evaluated after the build: nothing of it lives across the build
+            float best_v = -INFINITY;
+            int best_i = 0x7fffffff;
             // ---- drain this CTA's stages of the phase
-            float* out = (pk == 0) ? p.qkv : (pk == 2) ? p.hd : (pk == 4) ? p.logits : p.x1;
+            uint2* out = (pk == 0) ? p.qkvt : (pk == 2) ? p.hdt : p.x1t;
+            const uint32_t tag_out = tl + ((pk == 0) ? 1u : (pk == 1) ? 4u : (pk == 2) ? 5u : 6u);
             {
                 const int t0 = (int)((long long)ph.n_tasks * blockIdx.x / gridDim.x);
                 const int t1 = (int)((long long)ph.n_tasks * (blockIdx.x + 1) / gridDim.x);
                 const int spt_tile = ceil_div(ph.nkb, R::U), spt = ph.tt * spt_tile;
+                if (pf.p && traced && tid == kProfThread && pk >= 2) pf.p[28 + pk] = ld_shared_volatile_u32(issued) - sc;   // stages the producer is ahead
 #pragma unroll 1
                 for (int r0 = t0; r0 < t1; r0 += kConsumerWarps) {
                     const int nw = min(kConsumerWarps, t1 - r0);
                     if (warp < nw) {
+                        const int row = (r0 + warp) * 4 + r;
+                        // residual input of this row (x1 += tmp, tensor.cpp:723): its word was validated by an earlier build
+                        float x_old = 0.0f;
+                        if ((pk == 1 || pk == 3) && l == 0 && row < ph.M) x_old = __ldcg(reinterpret_cast<const float*>(p.x1t + row));
                         float acc = 0.0f, acc_first = 0.0f;
 #pragma unroll 1
                         for (int s = 0; s < spt; ++s) {
@@ -656,87 +865,91 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
                             const int tile = s / spt_tile, ks = s - tile * spt_tile, kb = ks * R::U;
                             const int nu = min(R::U, ph.nkb - kb);
                             if (tile == 1 && ks == 0) { acc_first = acc; acc = 0.0f; }       // W1 tile done, W3 tile starts
+                            pf.stop(tid, 2 + pk);
+                            while ((int)(ld_shared_volatile_u32(issued) - idx) <= 0) { }      // fact 4 in the header
                             mbar_wait(&full[slot], k & 1u);
+                            pf.stop(tid, 7);                                                  // waiting for weights = the stream is the limit
                             acc = stage_chain<QT, GS>(ring + (size_t)slot * R::SLOT_BYTES, nu, xq4 + (size_t)kb * (T::KB_BYTES / 16),
                                                       xs + kb * 8 * T::GPL, cs, lane, acc);
                             __syncwarp();
                             if (lane == 0) mbar_arrive(&empty[slot]);
                         }
-                        const int row = (r0 + warp) * 4 + r;
                         if (l == 0 && row < ph.M) {
                             float v;
                             if (pk == 0 || pk == 4) v = acc;
                             else if (pk == 2) v = swiglu_exact(acc_first, acc);
-                            else v = __fadd_rn(__ldcg(((pk == 1) ? x1_in : p.x1) + row), acc);     // x1 += tmp (tensor.cpp:723)
-                            out[row] = v;
-                            if (pk == 4 && (v > best_v || (v == best_v && row < best_i))) { best_v = v; best_i = row; }
+                            else v = __fadd_rn(x_old, acc);
+                            if (pk == 4) {
+                                p.logits[row] = v;
+                                if (v > best_v || (v == best_v && row < best_i)) { best_v = v; best_i = row; }
+                            } else {
+                                st_tag(out + row, v, tag_out);
+                            }
                         }
                     }
                     sc += (uint32_t)(nw * spt);
                 }
             }
             pf.stop(tid, 2 + pk);
-            if (pk == 4) break;
-            grid_barrier(p.bar_ctr, bar_target, tid);
-            pf.stop(tid, 0);
-            if (pk == 0) {
-                // ---- attention (transformer.cpp:136, :397-455)
-                if (attn_cta) {
-                    ++attn_rounds;
-                    attention_part<HS>(p, smem, layer, my_head, my_part, head_base + attn_rounds * (unsigned long long)p.cph, tid, pf);
+            if (pf.p && traced && lane == 0) atomicMax(pf.p + 24 + pk, gtimer());
+            if (pk == 4) {
+            // ---- argmax (sampler.cpp:36-46: first index of the strict maximum): per-CTA partial, exchanged as tagged words;
+            //      every CTA reduces all partials, so every CTA knows the next token without another round trip
+            {
+                const uint32_t tag_am = tbase + (uint32_t)p.n_layers * kTagsPerLayer + 1u;
+                float bv = best_v; int bi = best_i;
+    #pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float ov = __shfl_xor_sync(kFull, bv, o);
+                    const int oi = __shfl_xor_sync(kFull, bi, o);
+                    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
                 }
-                pf.stop(tid, 7);
-                grid_barrier(p.bar_ctr, bar_target, tid);
-                pf.stop(tid, 0);
+                float* sv = misc + 8; int* si = reinterpret_cast<int*>(misc + 16);
+                if (lane == 0) { sv[warp] = bv; si[warp] = bi; }
+                consumer_sync();
+                if (warp == 0) {
+                    if (lane == 0) {
+                        for (int w = 1; w < kConsumerWarps; ++w)
+                            if (sv[w] > bv || (sv[w] == bv && si[w] < bi)) { bv = sv[w]; bi = si[w]; }
+                        st_relaxed_v4(p.am + blockIdx.x, make_uint4(__float_as_uint(bv), tag_am, (uint32_t)bi, tag_am));
+                    }
+                    bv = -INFINITY; bi = 0x7fffffff;
+                    for (int i = lane; i < (int)gridDim.x; i += 32) {
+                        uint4 w = ld_relaxed_v4(p.am + i);
+                        while (w.y != tag_am || w.w != tag_am) w = ld_relaxed_v4(p.am + i);
+                        const float v = __uint_as_float(w.x); const int ix = (int)w.z;
+                        if (v > bv || (v == bv && ix < bi)) { bv = v; bi = ix; }
+                    }
+    #pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const float ov = __shfl_xor_sync(kFull, bv, o);
+                        const int oi = __shfl_xor_sync(kFull, bi, o);
+                        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+                    }
+                    if (lane == 0) {
+                        if (bi == 0x7fffffff) bi = 0;
+                        sstate[0] = bi;
+                        if (blockIdx.x == 0) {
+                            // sequence state for the host and the next launch
+                            SeqState* st = p.st;
+                            *p.argmax_out = bi;
+                            const int n_out = sstate[1];
+                            if (n_out < p.out_cap) p.out_tokens[n_out] = bi;
+                            st->n_out = n_out + 1; st->token = bi; st->pos = pos + 1; st->bs = 1;
+                            sstate[1] = n_out + 1;
+                        }
+                    }
+                }
+                consumer_sync();
+            }
+            }
+            if (pk == 0 && attn_cta) {
+                // ---- attention (transformer.cpp:136, :397-455)
+                consumer_sync();            // the V stage aliases the activation image the other warps may still be draining with
+                attention_part<HS>(p, smem, layer, my_head, my_part, pos, bs, tl + 1u, tl + 2u, tl + 3u, tid, pf);
             }
         }
-        // ---- argmax (sampler.cpp:36-46: first index of the strict maximum) and state advance
-        {
-            float bv = best_v; int bi = best_i;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const float ov = __shfl_xor_sync(kFull, bv, o);
-                const int oi = __shfl_xor_sync(kFull, bi, o);
-                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-            }
-            float* sv = misc + 8; int* si = reinterpret_cast<int*>(misc + 16);
-            if (lane == 0) { sv[warp] = bv; si[warp] = bi; }
-            consumer_sync();
-            if (tid == 0) {
-                for (int w = 1; w < kConsumerWarps; ++w)
-                    if (sv[w] > bv || (sv[w] == bv && si[w] < bi)) { bv = sv[w]; bi = si[w]; }
-                p.am_val[blockIdx.x] = bv; p.am_idx[blockIdx.x] = bi;
-            }
-        }
-        grid_barrier(p.bar_ctr, bar_target, tid);
-        if (blockIdx.x == 0 && warp == 0) {
-            float bv = -INFINITY; int bi = 0x7fffffff;
-            for (int i = lane; i < (int)gridDim.x; i += 32) {
-                const float v = __ldcg(p.am_val + i); const int ix = __ldcg(p.am_idx + i);
-                if (v > bv || (v == bv && ix < bi)) { bv = v; bi = ix; }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const float ov = __shfl_xor_sync(kFull, bv, o);
-                const int oi = __shfl_xor_sync(kFull, bi, o);
-                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-            }
-            if (lane == 0) {
-                if (bi == 0x7fffffff) bi = 0;
-                SeqState* st = p.st;
-                *p.argmax_out = bi;
-                const int no = __ldcg(&st->n_out);
-                if (no < p.out_cap) p.out_tokens[no] = bi;
-                st->n_out = no + 1; st->token = bi; st->pos = __ldcg(&st->pos) + 1; st->bs = 1;
-            }
-        }
-        grid_barrier(p.bar_ctr, bar_target, tid);      // the new state is visible to every CTA before the next token
-        pf.stop(tid, 0);
-    }
-    // publish the counter bases for the next launch (every CTA has passed the last barrier)
-    if (tid == 0) {
-        if (blockIdx.x == 0) p.bar_ctr[1] = bar_target - gridDim.x;
-        if (attn_cta && my_part == 0) p.head_ctr[p.n_heads + my_head] = head_base + attn_rounds * (unsigned long long)p.cph;
+        pf.stop(tid, 18);
     }
 }
 

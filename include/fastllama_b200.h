@@ -119,10 +119,11 @@ int   fl_sync(fl_engine* e);
  * sampled token): name in {"token","pos","argmax","out_tokens","logits"}; NULL if unknown. */
 void* fl_device_ptr(fl_engine* e, const char* name, int seq_slot);
 /* per-CTA nanoseconds spent per category by the persistent decode kernel since the last reset:
- * out[cta*32 + k], k = 0 grid barriers, 1 activation rebuild tail (after the rmsnorm chain / whole quantise), 2 QKV, 3 Wo,
- * 4 W1/W3, 5 W2, 6 classifier, 7 attention tail, 8 rebuild: loads + pre-products, 9 rebuild: sum-of-squares chain,
- * 10 attention: RoPE/append, 11 QK^T, 12 score exchange, 13 softmax, 14-17 PV (wait for V chunk, chain, issue next chunk, tail).  Needs FL_FLAG_PROFILE.
- * Returns the element count (32 * n_CTAs). */
+ * out[cta*32 + k], k = 0 waiting for tagged input words (exchange latency + slowest producer), 1 activation rebuild tail
+ * (quantise after the rmsnorm chain), 2 QKV, 3 Wo, 4 W1/W3, 5 W2, 6 classifier (weight-stream drains), 8 rebuild: products
+ * + transpose, 9 rebuild: sum-of-squares chain, 10 attention: q/k/v fetch + RoPE + append, 11 QK^T, 12 score exchange,
+ * 13 softmax, 14-17 PV (wait for V chunk, chain, issue next chunk, publish), 18 argmax exchange, 19 embedding row.
+ * Needs FL_FLAG_PROFILE.  Returns the element count (32 * n_CTAs). */
 int  fl_profile_read(fl_engine* e, uint64_t* out, int cap, int reset);
 /* number of kernels this engine has launched (graph nodes count once per replay) */
 int64_t fl_launch_count(const fl_engine* e);
