@@ -238,10 +238,14 @@ class Engine:
             raise FlError(f"fl_device_ptr: unknown name {name!r}")
         return p
 
-    def profile_read(self, reset=True):
-        buf = np.zeros(32 * 1024, np.uint64)
+    def profile_read(self, reset=True, events=False):
+        """per-CTA counters [n_ctas][32]; with events=True also the two event logs of the traced layer ([2][4096] uint64)"""
+        buf = np.zeros(32 * 1024 + 2 * 4096, np.uint64)
         n = _check(lib().fl_profile_read(self.h, _p(buf), buf.size, int(reset)), self.h)
-        return buf[:n].reshape(-1, 32).copy()
+        counters = buf[:n].reshape(-1, 32).copy()
+        if events:
+            return counters, buf[n:n + 2 * 4096].reshape(2, 4096).copy()
+        return counters
 
     def launch_count(self):
         return lib().fl_launch_count(self.h)

@@ -43,6 +43,13 @@ struct PackedMat {
     size_t bytes = 0;
 };
 
+// a matrix in the persistent kernel's "row per lane" streaming layout (megakernel.cuh)
+struct RkMat {
+    uint8_t* d = nullptr;
+    size_t bytes = 0;
+};
+enum { RK_QKV = 0, RK_WO, RK_W13, RK_W2, RK_CLS, RK__COUNT };
+
 }  // namespace
 
 struct fl_engine {
@@ -56,8 +63,13 @@ struct fl_engine {
     float* att_norm = nullptr;
     float* ffn_norm = nullptr;
     float* out_norm = nullptr;
-    std::vector<PackedMat> qkv, wo, w13, w2;
+    std::vector<PackedMat> qkv, wo, w13, w2;   // per-phase kernels' layout (FL_FLAG_NO_MEGAKERNEL only)
     PackedMat cls;
+    bool want_mega = false;                       // decided in fl_create: which of the two layouts the uploads fill
+    std::vector<RkMat> rk_qkv, rk_wo, rk_w13, rk_w2;
+    RkMat rk_cls;
+    unsigned long long* rk_off[RK__COUNT] = {};   // device: per-CTA stream offsets (n_sms + 1 entries), same for every layer
+    size_t rk_bytes[RK__COUNT] = {};
     std::vector<uint8_t> have;          // [kind][layer]
     uint8_t* staging = nullptr;
     size_t staging_bytes = 0;
@@ -84,6 +96,7 @@ struct fl_engine {
     uint4* am = nullptr;
     uint32_t epoch = 0;                 // last tag handed out (see megakernel.cuh)
     unsigned long long* prof = nullptr;
+    unsigned long long* evlog = nullptr;
     MegaParams mega{};
     size_t mega_smem = 0;
     bool finalized = false;
@@ -125,6 +138,40 @@ int alloc_packed(fl_engine* e, PackedMat& m, int rows_in_stream, int logical_row
     CK(e, cudaMalloc(&m.d, m.bytes));
     CK(e, cudaMemsetAsync(m.d, 0, m.bytes, e->stream));
     return FL_OK;
+}
+
+int rk_stage_bytes(int qt, int gs, int R) {
+    const int gps = (kStageRowBytes / es_of(qt)) / gs;
+    return R * kStageRowBytes + ((R * gps * 4 + 15) & ~15);
+}
+
+// per-CTA byte offsets of a matrix in the row-per-lane layout; must mirror pack_rk_kernel / the producer loop
+int build_rk_table(fl_engine* e, int kind, int M, int K, int tt) {
+    const int G = e->n_sms, qt = e->c.quant_type, gs = e->c.group_size;
+    const int nkc = ceil_div(K * es_of(qt), kStageRowBytes);
+    std::vector<unsigned long long> off(G + 1, 0);
+    for (int c = 0; c < G; ++c) {
+        const RkPart pt = rk_part(M, c, G);
+        unsigned long long bytes = 0;
+        for (int t = 0; t < pt.nt; ++t) { int lr0, R; rk_tile(pt, t, lr0, R); bytes += (unsigned long long)tt * nkc * rk_stage_bytes(qt, gs, R); }
+        off[c + 1] = off[c] + bytes;
+    }
+    e->rk_bytes[kind] = off[G];
+    CK(e, cudaMalloc(&e->rk_off[kind], sizeof(unsigned long long) * (G + 1)));
+    CK(e, cudaMemcpyAsync(e->rk_off[kind], off.data(), sizeof(unsigned long long) * (G + 1), cudaMemcpyHostToDevice, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    return FL_OK;
+}
+
+int alloc_rk(fl_engine* e, RkMat& m, int kind) {
+    m.bytes = e->rk_bytes[kind];
+    CK(e, cudaMalloc(&m.d, m.bytes + 256));
+    CK(e, cudaMemsetAsync(m.d, 0, m.bytes + 256, e->stream));
+    return FL_OK;
+}
+
+bool mega_supported(const fl_config& c, int n_sms) {
+    return !(c.flags & FL_FLAG_NO_MEGAKERNEL) && c.n_heads <= n_sms && c.dim <= 6144;
 }
 
 // dispatch helpers over (quant type, group size)
@@ -297,7 +344,7 @@ int setup_mega(fl_engine* e) {
     const int L = c.n_layers, qt = c.quant_type, gs = c.group_size, es = es_of(qt), gpl = 64 / gs;
     std::vector<MegaLayer> tab(L);
     for (int l = 0; l < L; ++l) {
-        tab[l].qkv = e->qkv[l].d; tab[l].wo = e->wo[l].d; tab[l].w13 = e->w13[l].d; tab[l].w2 = e->w2[l].d;
+        tab[l].qkv = e->rk_qkv[l].d; tab[l].wo = e->rk_wo[l].d; tab[l].w13 = e->rk_w13[l].d; tab[l].w2 = e->rk_w2[l].d;
         tab[l].att_norm = e->att_norm + (size_t)l * c.dim; tab[l].ffn_norm = e->ffn_norm + (size_t)l * c.dim;
     }
     CK(e, cudaMalloc(&e->mega_layers, sizeof(MegaLayer) * L));
@@ -319,34 +366,38 @@ int setup_mega(fl_engine* e) {
     CK(e, cudaMemsetAsync(e->am, 0, sizeof(uint4) * e->n_sms, e->stream));
     CK(e, cudaMalloc(&e->prof, sizeof(unsigned long long) * 32 * e->n_sms));
     CK(e, cudaMemsetAsync(e->prof, 0, sizeof(unsigned long long) * 32 * e->n_sms, e->stream));
+    CK(e, cudaMalloc(&e->evlog, sizeof(unsigned long long) * 2 * 4096));
+    CK(e, cudaMemsetAsync(e->evlog, 0, sizeof(unsigned long long) * 2 * 4096, e->stream));
     MegaParams& p = e->mega;
-    p.layers = e->mega_layers; p.cls = e->cls.d; p.out_norm = e->out_norm; p.emb = e->emb;
+    p.layers = e->mega_layers; p.cls = e->rk_cls.d; p.out_norm = e->out_norm; p.emb = e->emb;
+    p.off_qkv = e->rk_off[RK_QKV]; p.off_wo = e->rk_off[RK_WO]; p.off_w13 = e->rk_off[RK_W13]; p.off_w2 = e->rk_off[RK_W2]; p.off_cls = e->rk_off[RK_CLS];
     p.x1t = e->x1t; p.qkvt = e->qkvt; p.attnt = e->attnt; p.hdt = e->hdt; p.score_t = e->score_t; p.am = e->am; p.logits = e->logits;
     p.rope = e->rope; p.out_cap = e->out_cap; p.score_stride = score_stride;
     p.tap_norm = e->tap_norm; p.prof = (c.flags & FL_FLAG_PROFILE) ? e->prof : nullptr;
+    p.evlog = (c.flags & FL_FLAG_PROFILE) ? e->evlog : nullptr;
     p.dim = c.dim; p.hidden = c.hidden_dim; p.n_layers = L; p.n_heads = c.n_heads; p.n_kv_heads = c.n_kv_heads;
     p.vocab = c.vocab_size; p.max_seq = c.max_seq_len; p.qkv_rows = qkv_rows;
     p.attn_scale = 1.0f / sqrtf((float)c.head_size);
     const int cph = e->cph;
-    if (c.n_heads > e->n_sms) return set_err(e, FL_ERR_UNSUPPORTED, "megakernel: n_heads %d > SM count %d", c.n_heads, e->n_sms);
-    if (c.dim > 6144) return set_err(e, FL_ERR_UNSUPPORTED, "megakernel: dim %d > 6144 (the rmsnorm rebuild keeps the vector in registers)", c.dim);
     p.cph = cph;
     const int dw = c.head_size / cph;
     p.v_chunk_rows = 1024 / dw;                     // V chunks of 4 KB
     // shared memory carve-up
-    const int nkb_max = ceil_div(c.dim > c.hidden_dim ? c.dim : c.hidden_dim, kKBlockElems);
+    const int kmax = c.dim > c.hidden_dim ? c.dim : c.hidden_dim;
+    const int nkc_max = ceil_div(kmax * es, kStageRowBytes);
+    const int gps = (kStageRowBytes / es) / gs;
     auto al = [](size_t v, size_t a) { return (v + a - 1) / a * a; };
     size_t off = 0;
     p.off_misc = (int)off; off += 2048;
     p.off_att = (int)off; off += al((size_t)c.max_seq_len * 4 + 64, 128);
-    p.off_xs = (int)off; off += al((size_t)nkb_max * 8 * gpl * 4, 128);
+    p.off_xs = (int)off; off += al((size_t)nkc_max * gps * 4, 128);
     p.off_vbars = (int)off; off += 128;
-    // [chain slots | activation image | transposed fp32 vector]: contiguous, because attention (which uses none of them)
-    // turns the whole range into its ring of V chunks
-    const size_t chain_bytes = (size_t)kConsumerWarps * (qt == FL_Q_INT8 ? 4 : 2) * 32 * 2 * gpl * 4;   // one stage of (s, f) pairs per warp
-    const size_t xq_bytes = al((size_t)nkb_max * kKBlockElems * es, 128), xt_bytes = al((size_t)c.dim * 4, 128);
+    p.off_tok = (int)off; off += kConsumerWarps * 2 * 32 * 4 + 128;      // chain-token inboxes + their counters
+    // [activation image | transposed fp32 vector]: contiguous, because attention (which uses neither) turns the whole
+    // range into its ring of V chunks
+    const size_t xq_bytes = al((size_t)nkc_max * kStageRowBytes, 128), xt_bytes = al((size_t)c.dim * 4, 128);
     p.off_vstage = (int)off;
-    p.off_chain = (int)off; off += chain_bytes;
+    p.off_chain = (int)off;
     p.off_xq = (int)off; off += xq_bytes;
     p.off_xt = (int)off; off += xt_bytes;
     size_t vbytes = off - p.off_vstage;
@@ -354,7 +405,7 @@ int setup_mega(fl_engine* e) {
     p.n_vchunks = (int)(vbytes / 4096) > 16 ? 16 : (int)(vbytes / 4096);
     int max_smem = 0;
     CK(e, cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, e->device));
-    const size_t slot_bytes = (size_t)(qt == FL_Q_INT8 ? 4 : 2) * unit_bytes(qt, gs);
+    const size_t slot_bytes = (size_t)rk_stage_bytes(qt, gs, kTileRows);
     int n_slots = (int)(((size_t)max_smem - off - 1024) / (slot_bytes + 16));
     if (n_slots > 32) n_slots = 32;
     if (n_slots < 4) return set_err(e, FL_ERR_UNSUPPORTED, "megakernel: not enough shared memory for the weight ring (%d slots)", n_slots);
@@ -491,14 +542,32 @@ int fl_create(const fl_config* cfg, int device, fl_engine** out) {
     CKF(cudaMalloc(&e->att_norm, (size_t)L * c.dim * 4));
     CKF(cudaMalloc(&e->ffn_norm, (size_t)L * c.dim * 4));
     CKF(cudaMalloc(&e->out_norm, (size_t)c.dim * 4));
-    for (int l = 0; l < L; ++l) {
-        int rc = alloc_packed(e, e->qkv[l], c.dim + 2 * kv_dim, c.dim + 2 * kv_dim, c.dim);
-        if (!rc) rc = alloc_packed(e, e->wo[l], c.dim, c.dim, c.dim);
-        if (!rc) rc = alloc_packed(e, e->w13[l], 2 * ceil_div(c.hidden_dim, 4) * 4, c.hidden_dim, c.dim);
-        if (!rc) rc = alloc_packed(e, e->w2[l], c.dim, c.dim, c.hidden_dim);
+    e->want_mega = mega_supported(c, e->n_sms);
+    if (e->want_mega) {
+        e->rk_qkv.resize(L); e->rk_wo.resize(L); e->rk_w13.resize(L); e->rk_w2.resize(L);
+        int rc = build_rk_table(e, RK_QKV, c.dim + 2 * kv_dim, c.dim, 1);
+        if (!rc) rc = build_rk_table(e, RK_WO, c.dim, c.dim, 1);
+        if (!rc) rc = build_rk_table(e, RK_W13, c.hidden_dim, c.dim, 2);
+        if (!rc) rc = build_rk_table(e, RK_W2, c.dim, c.hidden_dim, 1);
+        if (!rc) rc = build_rk_table(e, RK_CLS, c.vocab_size, c.dim, 1);
+        for (int l = 0; l < L && !rc; ++l) {
+            rc = alloc_rk(e, e->rk_qkv[l], RK_QKV);
+            if (!rc) rc = alloc_rk(e, e->rk_wo[l], RK_WO);
+            if (!rc) rc = alloc_rk(e, e->rk_w13[l], RK_W13);
+            if (!rc) rc = alloc_rk(e, e->rk_w2[l], RK_W2);
+        }
+        if (!rc) rc = alloc_rk(e, e->rk_cls, RK_CLS);
         if (rc) return fail(rc);
+    } else {
+        for (int l = 0; l < L; ++l) {
+            int rc = alloc_packed(e, e->qkv[l], c.dim + 2 * kv_dim, c.dim + 2 * kv_dim, c.dim);
+            if (!rc) rc = alloc_packed(e, e->wo[l], c.dim, c.dim, c.dim);
+            if (!rc) rc = alloc_packed(e, e->w13[l], 2 * ceil_div(c.hidden_dim, 4) * 4, c.hidden_dim, c.dim);
+            if (!rc) rc = alloc_packed(e, e->w2[l], c.dim, c.dim, c.hidden_dim);
+            if (rc) return fail(rc);
+        }
+        { int rc = alloc_packed(e, e->cls, c.vocab_size, c.vocab_size, c.dim); if (rc) return fail(rc); }
     }
-    { int rc = alloc_packed(e, e->cls, c.vocab_size, c.vocab_size, c.dim); if (rc) return fail(rc); }
     const int es = es_of(c.quant_type);
     size_t max_elems = (size_t)c.vocab_size * c.dim;
     if ((size_t)c.hidden_dim * c.dim > max_elems) max_elems = (size_t)c.hidden_dim * c.dim;
@@ -547,10 +616,16 @@ void fl_destroy(fl_engine* e) {
     for (auto& m : e->w13) fr(m.d);
     for (auto& m : e->w2) fr(m.d);
     fr(e->cls.d); fr(e->staging);
+    for (auto& m : e->rk_qkv) fr(m.d);
+    for (auto& m : e->rk_wo) fr(m.d);
+    for (auto& m : e->rk_w13) fr(m.d);
+    for (auto& m : e->rk_w2) fr(m.d);
+    fr(e->rk_cls.d);
+    for (int k = 0; k < RK__COUNT; ++k) fr(e->rk_off[k]);
     fr(e->x1); fr(e->qkv_buf); fr(e->attn); fr(e->hd); fr(e->logits); fr(e->tap_qkv); fr(e->tap_norm);
     fr(e->k_cache); fr(e->v_cache); fr(e->rope); fr(e->states); fr(e->out_tokens); fr(e->in_tokens); fr(e->argmax_dev);
     fr(e->ag_send); fr(e->ag_recv);
-    fr(e->mega_layers); fr(e->x1t); fr(e->qkvt); fr(e->attnt); fr(e->hdt); fr(e->score_t); fr(e->am); fr(e->prof);
+    fr(e->mega_layers); fr(e->x1t); fr(e->qkvt); fr(e->attnt); fr(e->hdt); fr(e->score_t); fr(e->am); fr(e->prof); fr(e->evlog);
     if (e->h_tokens) cudaFreeHost(e->h_tokens);
     if (e->h_logits) cudaFreeHost(e->h_logits);
     if (e->h_argmax) cudaFreeHost(e->h_argmax);
@@ -599,6 +674,26 @@ int fl_upload(fl_engine* e, int kind, int layer, const void* q, const float* sca
             // dequantised once here; the reference dequantises the row per token (transformer.cpp:117-118), same bits
             dequant_rows_kernel<<<1024, 256, 0, e->stream>>>(e->staging, d_scales, e->emb, n, gs, qt);
         } else {
+            if (e->want_mega) {
+                RkMat* m = nullptr;
+                int kindk = 0, m_total = rows, row_base = 0, tt = 1, sub = 0;
+                switch (kind) {
+                    case FL_T_WQ: m = &e->rk_qkv[layer]; kindk = RK_QKV; m_total = c.dim + 2 * kv_dim; break;
+                    case FL_T_WK: m = &e->rk_qkv[layer]; kindk = RK_QKV; m_total = c.dim + 2 * kv_dim; row_base = c.dim; break;
+                    case FL_T_WV: m = &e->rk_qkv[layer]; kindk = RK_QKV; m_total = c.dim + 2 * kv_dim; row_base = c.dim + kv_dim; break;
+                    case FL_T_WO: m = &e->rk_wo[layer]; kindk = RK_WO; break;
+                    case FL_T_W1: m = &e->rk_w13[layer]; kindk = RK_W13; tt = 2; break;
+                    case FL_T_W3: m = &e->rk_w13[layer]; kindk = RK_W13; tt = 2; sub = 1; break;
+                    case FL_T_W2: m = &e->rk_w2[layer]; kindk = RK_W2; break;
+                    case FL_T_CLS: m = &e->rk_cls; kindk = RK_CLS; break;
+                }
+                int rc = dispatch_q(qt, gs, [&](auto QT, auto GS) -> int {
+                    pack_rk_kernel<decltype(QT)::value, decltype(GS)::value><<<dim3(e->n_sms, 16), 256, 0, e->stream>>>(
+                        e->staging, d_scales, m->d, e->rk_off[kindk], m_total, cols, row_base, rows, tt, sub);
+                    return FL_OK;
+                });
+                if (rc) return set_err(e, rc, "fl_upload: unsupported quantisation");
+            } else {
             PackedMat* m = nullptr;
             int tile_offset = 0, tile_stride = 1;
             switch (kind) {
@@ -618,6 +713,7 @@ int fl_upload(fl_engine* e, int kind, int layer, const void* q, const float* sca
                 return FL_OK;
             });
             if (rc) return set_err(e, rc, "fl_upload: unsupported quantisation");
+            }
         }
         CK(e, cudaGetLastError());
         CK(e, cudaStreamSynchronize(e->stream));
@@ -643,7 +739,7 @@ int fl_finalize(fl_engine* e) {
     CK(e, cudaMemcpyAsync(e->rope, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice, e->stream));
     CK(e, cudaStreamSynchronize(e->stream));
     if (e->staging) { cudaFree(e->staging); e->staging = nullptr; }
-    if (!(c.flags & FL_FLAG_NO_MEGAKERNEL)) {
+    if (e->want_mega) {
         int rc = setup_mega(e);
         if (rc) return rc;
         e->use_mega = true;
@@ -760,7 +856,15 @@ int fl_profile_read(fl_engine* e, uint64_t* out, int cap, int reset) {
     CK(e, cudaStreamSynchronize(e->stream));
     CK(e, cudaMemcpyAsync(out, e->prof, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost, e->stream));
     CK(e, cudaStreamSynchronize(e->stream));
-    if (reset) { CK(e, cudaMemsetAsync(e->prof, 0, sizeof(uint64_t) * n, e->stream)); CK(e, cudaStreamSynchronize(e->stream)); }
+    if (cap >= n + 2 * 4096 && e->evlog) {      // optional: the event log of the traced layer follows the counters
+        CK(e, cudaMemcpyAsync(out + n, e->evlog, sizeof(uint64_t) * 2 * 4096, cudaMemcpyDeviceToHost, e->stream));
+        CK(e, cudaStreamSynchronize(e->stream));
+    }
+    if (reset) {
+        CK(e, cudaMemsetAsync(e->prof, 0, sizeof(uint64_t) * n, e->stream));
+        if (e->evlog) CK(e, cudaMemsetAsync(e->evlog, 0, sizeof(uint64_t) * 2 * 4096, e->stream));
+        CK(e, cudaStreamSynchronize(e->stream));
+    }
     return n;
 }
 

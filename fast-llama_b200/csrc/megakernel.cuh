@@ -20,8 +20,18 @@
 //   * attention runs between the QKV and Wo phases on n_heads * CPH CTAs (CPH CTAs share one head: keys are split for
 //     QK^T, head dims are split for the PV chains), exchanging the score vector through L2 the same way.
 //
-// Each CTA owns a contiguous range of 4-row tiles of every matrix (rows/148 +- 4), so its share of a phase is ONE
-// contiguous byte range of the streaming layout and every stage is a single bulk copy.
+// Weight layout ("row per lane", packed once at upload): CTA c owns rows [M*c/G, M*(c+1)/G) of every matrix, cut into
+// tiles of <= 32 rows, ONE LANE PER ROW.  A stage is 256 bytes of every row of a tile plus the rows' group scales, stored
+// piece-major so lane i's 16-byte piece sits next to lane i+1's (conflict-free LDS.128), and a CTA's stages lie in HBM in
+// exactly the order its producer issues them - its share of a phase is one contiguous byte range.
+// All 8 consumer warps work on the SAME tile: the K range is cut into 8 consecutive blocks, warp w computes, for its
+// block, every row's integer group dots (exact in any order) and scale products into registers.  The reference's FP32
+// chain over groups (quant_operators.cpp:274) is strictly sequential, so it travels as a TOKEN: warp 0 runs the chain over
+// its block, hands the 32 partial sums to warp 1 through shared memory, and so on; the last warp writes the rows.  The
+// expensive part (loads + dp4a) is fully parallel, the serial part is 4.5 cycles per group plus 7 hand-offs per tile,
+// and while the token of tile t travels the early warps already work on tile t+1.
+// (History, profiles/r01: a 4-rows-x-8-lanes layout that transposed (scale, dot) pairs through shared memory ran at
+// 1500 cycles per 8.7 KB stage per warp - slower than HBM; one warp per tile over the whole K was starved by ILP.)
 //
 // Hardware facts that shape the code (all measured, see DESIGN.md "What the profiler taught us"):
 //   1. With ~227 KB of shared memory carved out there is practically no L1 left: every local-memory (stack) access and
@@ -57,6 +67,7 @@ struct MegaParams {
     const uint8_t* cls;
     const float* out_norm;
     const float* emb;
+    const unsigned long long *off_qkv, *off_wo, *off_w13, *off_w2, *off_cls;   // per-CTA stream offsets inside the packed matrices
     uint2* x1t; uint2* qkvt; uint2* attnt; uint2* hdt;   // tagged activation vectors: word i = (float bits, tag)
     uint2* score_t;                   // [n_heads][score_stride] tagged raw scores exchanged between the CTAs of a head
     uint4* am;                        // [gridDim] argmax partials (value bits, tag, index, tag)
@@ -67,6 +78,7 @@ struct MegaParams {
     int* out_tokens; int out_cap; int* argmax_out;
     float* tap_norm;
     unsigned long long* prof;         // optional [gridDim][32] ns per category, see fl_profile_read
+    unsigned long long* evlog;        // optional event log of the traced layer on CTAs 7 and gridDim-3: [2][4096] {count | (ns << 24 | warp << 20 | type << 12 | arg)}
     int dim, hidden, n_layers, n_heads, n_kv_heads, vocab, max_seq;
     int qkv_rows;
     int score_stride;
@@ -77,7 +89,7 @@ struct MegaParams {
     int window;                       // max stages in flight (issued, not yet landed); >= n_slots: no limit
     uint32_t epoch;                   // tags of this launch are epoch + 1 ... epoch + n_steps * (n_layers + 1) * 8
     // dynamic shared memory carve-up (byte offsets)
-    int off_ring, off_xq, off_xs, off_xt, off_chain, off_att, off_misc, off_bars, off_vstage, off_vbars;
+    int off_ring, off_xq, off_xs, off_xt, off_chain, off_att, off_misc, off_bars, off_vstage, off_vbars, off_tok;
     int v_chunk_rows, n_vchunks;     // V ring of the attention part: n_vchunks chunks of v_chunk_rows rows x HS/cph floats
 };
 
@@ -149,49 +161,134 @@ __device__ __forceinline__ void st_relaxed_v4(uint4* p, uint4 v) {
 
 // per-CTA phase timing, only when MegaParams::prof is set; lives in registers.  Thread kProfThread keeps the clock.
 struct Prof {
-    unsigned long long* p; unsigned long long t0; int trace_slot;   // trace_slot >= 0: the current build records when its input was complete
+    unsigned long long* p; unsigned long long t0; int trace_slot;
+    unsigned long long* ev;           // event log of this CTA while the traced layer runs, else NULL
+    __device__ __forceinline__ void log(int lane, int warp, int type, int arg) {
+        if (ev && lane == 0) { const unsigned long long i = atomicAdd(ev, 1ull); if (i < 4095) ev[1 + i] = (gtimer() << 24) | ((unsigned long long)warp << 20) | ((unsigned long long)type << 12) | (unsigned long long)(arg & 0xfff); }
+    }   // trace_slot >= 0: the current build records when its input was complete
     __device__ __forceinline__ void stop(int tid, int cat) {
         if (p && tid == kProfThread) { const unsigned long long t = gtimer(); atomicAdd(p + cat, t - t0); t0 = t; }
     }
-    // absolute timestamp of one event of the traced layer (slots 20..31): skew and latency of one exchange, see profiles/trace_layer.py
+    // absolute timestamp of one event of the traced layer (slots 22..31): skew and latency of one exchange, see profiles/trace_layer.py
     __device__ __forceinline__ void mark(int tid, int slot, bool on) {
         if (p && on && tid == kProfThread) p[slot] = gtimer();
     }
 };
 
 // ---------------------------------------------------------------------------------------------- schedule
+constexpr int kStageRowBytes = 256;        // bytes of one row in one stage
+constexpr int kTileRows = 32;              // one lane per row
+
 template <int QT, int GS>
-struct Ring {
-    using T = Traits<QT, GS>;
-    static constexpr int U = (QT == Q_INT8) ? 4 : 2;             // units per stage
-    static constexpr int SLOT_BYTES = U * T::UNIT_BYTES;
+struct Rk {
+    static constexpr int ES = (QT == Q_INT8) ? 1 : 2;            // element bytes
+    static constexpr int EPS = kStageRowBytes / ES;               // elements of a row per stage
+    static constexpr int GPS = EPS / GS;                          // quantisation groups of a row per stage
+    static constexpr int PPG = GS * ES / 16;                      // 16-byte pieces per group
+    static constexpr int PIECES = kStageRowBytes / 16;
+    __host__ __device__ static constexpr int stage_bytes(int R) { return R * kStageRowBytes + ((R * GPS * 4 + 15) & ~15); }
+    static constexpr int SLOT_BYTES = stage_bytes(kTileRows);
+    static_assert(GS == 64 || (GS == 32 && QT == Q_INT8), "group size");
 };
 
-// Phase p of a token (p = 4*layer + {0 QKV, 1 Wo, 2 W1/W3, 3 W2}, p = 4*n_layers: classifier): where its weights are
-// and how they are cut into tasks (row tiles / W1-W3 tile pairs).  Pure function of (params, p): the producer and
-// every consumer warp evaluate it independently and must agree.
+// rows of CTA c and their cut into tiles (host and device agree on this arithmetic; the packer bakes it into the layout)
+struct RkPart { int rb, nr, nt; };
+__host__ __device__ inline RkPart rk_part(int M, int c, int G) {
+    RkPart r;
+    r.rb = (int)((long long)M * c / G);
+    r.nr = (int)((long long)M * (c + 1) / G) - r.rb;
+    r.nt = (r.nr + kTileRows - 1) / kTileRows;
+    return r;
+}
+__host__ __device__ inline void rk_tile(const RkPart& pt, int t, int& lr0, int& R) {
+    lr0 = pt.nr * t / pt.nt;
+    R = pt.nr * (t + 1) / pt.nt - lr0;
+}
+
+// K split of a tile: the nkc stages (K chunks) are cut into nsb superblocks; inside a superblock of S chunks warp w owns
+// the consecutive chunks [w*base + min(w, rem), ...) (base = S/8, rem = S%8, the first `rem` warps own one more) and keeps
+// their (scale product, dot) pairs in registers - at most kMaxPairs per lane, which bounds the superblock.
+constexpr int kMaxPairs = 24;
+__host__ __device__ inline int rk_bmax(int gps, int tt) {          // stages per warp per superblock, per sub-stream
+    int b = kMaxPairs / gps;
+    if (b > 4) b = 4;
+    if (tt == 2) b = b / 2;
+    return b < 1 ? 1 : b;
+}
+__host__ __device__ inline int rk_nsb(int nkc, int gps, int tt) { return (nkc + kConsumerWarps * rk_bmax(gps, tt) - 1) / (kConsumerWarps * rk_bmax(gps, tt)); }
+__host__ __device__ inline void rk_superblock(int nkc, int nsb, int j, int& k0, int& S) { k0 = nkc * j / nsb; S = nkc * (j + 1) / nsb - k0; }
+
+// Pack rows [row_base, row_base + rows_src) of the logical matrix (M_total rows; `tt` sub-streams, this source is
+// sub-stream `m`: W1 = 0 / W3 = 1 of the fused W13 matrix) from the reference's row-major payload + scale table.
+// CTA stream order = issue order: [tile][superblock][i][warp][m]; stage = pieces p = 0..15 x R lanes x 16 B, then scales g x R.
+template <int QT, int GS>
+__global__ void pack_rk_kernel(const uint8_t* __restrict__ raw, const float* __restrict__ scales, uint8_t* __restrict__ packed,
+                               const unsigned long long* __restrict__ cta_off, int M_total, int K, int row_base, int rows_src, int tt, int m) {
+    using RK = Rk<QT, GS>;
+    const int c = blockIdx.x, G = gridDim.x;
+    const RkPart pt = rk_part(M_total, c, G);
+    const int kbytes = K * RK::ES, nkc = (kbytes + kStageRowBytes - 1) / kStageRowBytes, Gtot = K / GS;
+    const int nsb = rk_nsb(nkc, RK::GPS, tt);
+    uint8_t* tile_base = packed + cta_off[c];
+    for (int t = 0; t < pt.nt; ++t) {
+        int lr0, R;
+        rk_tile(pt, t, lr0, R);
+        const int sb = RK::stage_bytes(R);
+        for (int kc = blockIdx.y; kc < nkc; kc += gridDim.y) {
+            // which (superblock, warp, i) streams this K chunk
+            int j = 0, k0 = 0, S = 0;
+            for (; j < nsb; ++j) { rk_superblock(nkc, nsb, j, k0, S); if (kc < k0 + S) break; }
+            const int q = kc - k0, base = S >> 3, rem = S & 7;
+            int w, i;
+            if (q < rem * (base + 1)) { w = q / (base + 1); i = q - w * (base + 1); }
+            else { const int q2 = q - rem * (base + 1); w = rem + q2 / base; i = q2 - (w - rem) * base; }
+            const size_t stage_in_tile = (size_t)(k0 + i * kConsumerWarps + w) * tt + m;
+            uint8_t* st = tile_base + stage_in_tile * sb;
+            const int n_items = R * RK::PIECES + R * RK::GPS;
+            for (int idx = threadIdx.x; idx < n_items; idx += blockDim.x) {
+                if (idx < R * RK::PIECES) {
+                    const int pc = idx / R, lane = idx - pc * R;
+                    const int srow = pt.rb + lr0 + lane - row_base;
+                    if (srow < 0 || srow >= rows_src) continue;
+                    const int eb = kc * kStageRowBytes + pc * 16;
+                    uint4 v = make_uint4(0, 0, 0, 0);
+                    if (eb < kbytes) v = *reinterpret_cast<const uint4*>(raw + (size_t)srow * kbytes + eb);
+                    *reinterpret_cast<uint4*>(st + (size_t)idx * 16) = v;
+                } else {
+                    const int si = idx - R * RK::PIECES, g = si / R, lane = si - g * R;
+                    const int srow = pt.rb + lr0 + lane - row_base;
+                    if (srow < 0 || srow >= rows_src) continue;
+                    const int gi = kc * RK::GPS + g;
+                    *reinterpret_cast<float*>(st + (size_t)R * kStageRowBytes + (size_t)si * 4) = gi < Gtot ? scales[(size_t)srow * Gtot + gi] : 0.0f;
+                }
+            }
+        }
+        tile_base += (size_t)nkc * tt * sb;
+    }
+}
+
+// Phase p of a token (p = 4*layer + {0 QKV, 1 Wo, 2 W1/W3, 3 W2}, p = 4*n_layers: classifier): where its weights are and how
+// they are cut.  Pure function of (params, p): the producer and every consumer warp evaluate it independently and agree.
 struct PhaseShape {
-    const uint8_t* w;
-    int n_tasks;          // row tiles (or W1/W3 tile pairs)
-    int tt;               // row tiles per task (2 for the interleaved W1/W3 stream)
-    int nkb;              // K-blocks (units) per row tile; a stage never straddles two tiles
-    int K;                // input length
-    int M;                // output rows
+    const uint8_t* w;                  // packed matrix
+    const unsigned long long* off;     // byte offset of every CTA's stream inside it
+    int tt;                            // sub-streams per tile (2 for the fused W1/W3 matrix)
+    int K;                             // input length
+    int M;                             // output rows
 };
 
 __device__ __forceinline__ PhaseShape phase_shape(const MegaParams& p, int pi) {
-    const int nkb_d = ceil_div(p.dim, kKBlockElems), nkb_h = ceil_div(p.hidden, kKBlockElems);
     PhaseShape s;
     if (pi == 4 * p.n_layers) {
-        s.w = p.cls; s.n_tasks = ceil_div(p.vocab, 4); s.tt = 1; s.nkb = nkb_d; s.K = p.dim; s.M = p.vocab;
+        s.w = p.cls; s.off = p.off_cls; s.tt = 1; s.K = p.dim; s.M = p.vocab;
         return s;
     }
     const MegaLayer* L = p.layers + (pi >> 2);
     const int ph = pi & 3;
-    if (ph == 0)      { s.w = L->qkv; s.n_tasks = ceil_div(p.qkv_rows, 4); s.tt = 1; s.nkb = nkb_d; s.K = p.dim;    s.M = p.qkv_rows; }
-    else if (ph == 1) { s.w = L->wo;  s.n_tasks = ceil_div(p.dim, 4);      s.tt = 1; s.nkb = nkb_d; s.K = p.dim;    s.M = p.dim; }
-    else if (ph == 2) { s.w = L->w13; s.n_tasks = ceil_div(p.hidden, 4);   s.tt = 2; s.nkb = nkb_d; s.K = p.dim;    s.M = p.hidden; }
-    else              { s.w = L->w2;  s.n_tasks = ceil_div(p.dim, 4);      s.tt = 1; s.nkb = nkb_h; s.K = p.hidden; s.M = p.dim; }
+    if (ph == 0)      { s.w = L->qkv; s.off = p.off_qkv; s.tt = 1; s.K = p.dim;    s.M = p.qkv_rows; }
+    else if (ph == 1) { s.w = L->wo;  s.off = p.off_wo;  s.tt = 1; s.K = p.dim;    s.M = p.dim; }
+    else if (ph == 2) { s.w = L->w13; s.off = p.off_w13; s.tt = 2; s.K = p.dim;    s.M = p.hidden; }
+    else              { s.w = L->w2;  s.off = p.off_w2;  s.tt = 1; s.K = p.hidden; s.M = p.dim; }
     return s;
 }
 
@@ -204,8 +301,7 @@ __device__ __forceinline__ float group_max8(float m) {
 }
 
 // quantise one lane's share of a group (PER consecutive values, 8 lanes per group) given the group's max |value|:
-// quant::quantize (quant_operators.cpp:26-47).  The PER values are PER consecutive elements of one 16-byte chunk of
-// the permuted image, so they are packed and stored as words.
+// quant::quantize (quant_operators.cpp:26-47); packed and stored as words.
 template <int QT, int GS>
 __device__ __forceinline__ void quant_store(uint8_t* xq, float* xs, const float (&y)[GS / 8], float m, int g, int sub, float* tap) {
     constexpr int PER = GS / 8;
@@ -220,7 +316,7 @@ __device__ __forceinline__ void quant_store(uint8_t* xq, float* xs, const float 
         const uint32_t q = (uint32_t)cvtt_x86(__fdiv_rn(y[i], sc)) & ((QT == Q_INT8) ? 0xffu : 0xffffu);
         pk[i / EPW] = (i % EPW == 0) ? q : (pk[i / EPW] | (q << ((32 / EPW) * (i % EPW))));
     }
-    uint32_t* dst = reinterpret_cast<uint32_t*>(xq + x_perm_offset<QT, GS>(e0));
+    uint32_t* dst = reinterpret_cast<uint32_t*>(xq + (size_t)e0 * ((QT == Q_INT8) ? 1 : 2));     // natural element order
 #pragma unroll
     for (int i = 0; i < PER / EPW; ++i) dst[i] = pk[i];
     if (tap) {
@@ -282,14 +378,14 @@ __device__ __forceinline__ float sumsq_chain_t(const float* xt, int n, int lane)
 // registers while warp 0 walks the sum-of-squares chain (max |(x*w)*r| == (max |x*w|)*r: rounding is monotonic, r > 0).
 template <int QT, int GS>
 __device__ __forceinline__ void build_activation(uint8_t* xq, float* xs, float* xt, float* misc, const uint2* src, uint32_t tag,
-                                                 const float* gain, int K, int nkb, float* tap, int tid, Prof& pf) {
-    using T = Traits<QT, GS>;
+                                                 const float* gain, int K, float* tap, int tid, Prof& pf) {
+    using RK = Rk<QT, GS>;
     constexpr int PER = GS / 8;                 // values per thread per group
     constexpr int LPP = PER / 2;                // 16-byte loads per thread per pass
     constexpr int GPP = kConsumerThreads / 8;   // groups per pass
     constexpr int MAXP = 24 / PER;              // passes per batch (24 values per thread: registers, not shared memory)
     const int warp = tid >> 5, lane = tid & 31;
-    const int kpad = nkb * kKBlockElems;
+    const int kpad_bytes = ceil_div(K * RK::ES, kStageRowBytes) * kStageRowBytes;      // the image is padded to whole stages
     const int G = K / GS;
     const int sub = tid & 7, g0 = tid >> 3;
     const int n_pass = ceil_div(G, GPP);
@@ -323,15 +419,17 @@ __device__ __forceinline__ void build_activation(uint8_t* xq, float* xs, float* 
                         if (w[ps][q].y != tag || w[ps][q].w != tag) { w[ps][q] = ld_tag2(s + 2 * q); again = true; }
                 }
             }
+            if (again) __nanosleep(100);        // a poll that failed is not worth repeating at once: the LSU is shared with warps still working
         } while (again);
         pf.stop(tid, 0);
+        pf.log(tid & 31, tid >> 5, 9, b0);
         if (b0 + MAXP >= n_pass) pf.mark(tid, pf.trace_slot, pf.trace_slot >= 0);
         if (b0 == 0) {
             // every warp has left the previous phase (its drain / attention read the image this build overwrites)
             consumer_sync();
             // zero the padded tail so padded groups contribute fma(0, 0, acc) == acc
-            for (int i = K * T::ES + tid * 4; i < kpad * T::ES; i += kConsumerThreads * 4) *reinterpret_cast<uint32_t*>(xq + i) = 0u;
-            for (int i = G + tid; i < nkb * 8 * T::GPL; i += kConsumerThreads) xs[i] = 0.0f;
+            for (int i = K * RK::ES + tid * 4; i < kpad_bytes; i += kConsumerThreads * 4) *reinterpret_cast<uint32_t*>(xq + i) = 0u;
+            for (int i = G + tid; i < (kpad_bytes / kStageRowBytes) * RK::GPS; i += kConsumerThreads) xs[i] = 0.0f;
         }
         float y[MAXP][PER];
         float m[MAXP];
@@ -401,52 +499,26 @@ __device__ __forceinline__ void build_activation(uint8_t* xq, float* xs, float* 
 }
 
 // ---------------------------------------------------------------------------------------------- consumer GEMV phase
-// One stage = up to U consecutive units of one row tile.  Pass 1 (independent work, lots of ILP): integer dots of all
-// units of the stage, (scale product, float(dot)) pairs into the warp's shared-memory slot.  Pass 2: every lane of a
-// row walks its row's pairs in group order — the reference's FP32 chain fma(s, f, acc) (quant_operators.cpp:274-275).
+// One stage = 256 bytes of each of the R rows of a tile.  Lane i owns row i: integer dots of its GPS groups (exact, any
+// order) and the scale products ws * xs, kept for the chain  acc = fma(ws * xs, float(dot), acc)  (quant_operators.cpp:274-275).
+// xp / xsp: the activation image and scales of this K chunk (same for all lanes: broadcast loads).
 template <int QT, int GS>
-__device__ __forceinline__ float stage_chain(const uint8_t* sp, int nu, const uint4* xk, const float* xsk, float* cs, int lane, float acc) {
-    using T = Traits<QT, GS>;
-    using R = Ring<QT, GS>;
-    const int l = lane & 7, r = lane >> 3;
-    constexpr int PW = 2 * T::GPL;                 // floats per lane per unit in the slot
+__device__ __forceinline__ void stage_pairs(const uint8_t* sp, int R, const uint4* xp, const float* xsp, int lane,
+                                            float (&prod)[Rk<QT, GS>::GPS], float (&fdot)[Rk<QT, GS>::GPS]) {
+    using RK = Rk<QT, GS>;
+    const uint4* wp = reinterpret_cast<const uint4*>(sp) + lane;
+    const float* ssp = reinterpret_cast<const float*>(sp + R * kStageRowBytes) + lane;
 #pragma unroll
-    for (int u = 0; u < R::U; ++u) {
-        if (u < nu) {
-            const uint8_t* up = sp + (size_t)u * T::UNIT_BYTES;
-            int dj[T::NJ];
+    for (int g = 0; g < RK::GPS; ++g) {
+        int dj[RK::PPG];
 #pragma unroll
-            for (int j = 0; j < T::NJ; ++j)
-                dj[j] = dot16<QT>(reinterpret_cast<const uint4*>(up)[j * 32 + lane], xk[(size_t)u * (T::KB_BYTES / 16) + j * 8 + l], 0);
-            int d[T::GPL];
+        for (int j = 0; j < RK::PPG; ++j) dj[j] = dot16<QT>(wp[(g * RK::PPG + j) * R], xp[g * RK::PPG + j], 0);
+        int d = dj[0];
 #pragma unroll
-            for (int gg = 0; gg < T::GPL; ++gg) d[gg] = 0;
-#pragma unroll
-            for (int j = 0; j < T::NJ; ++j) d[(j * 16) / (GS * T::ES)] += dj[j];
-            const float* wsp = reinterpret_cast<const float*>(up + T::W_BYTES) + lane * T::GPL;
-            float* dst = cs + (size_t)(u * 32 + lane) * PW;
-            if (T::GPL == 1) {
-                *reinterpret_cast<float2*>(dst) = make_float2(__fmul_rn(wsp[0], xsk[u * 8 + l]), __int2float_rn(d[0]));
-            } else {
-                *reinterpret_cast<float4*>(dst) = make_float4(__fmul_rn(wsp[0], xsk[(u * 8 + l) * 2]), __int2float_rn(d[0]),
-                                                              __fmul_rn(wsp[T::GPL - 1], xsk[(u * 8 + l) * 2 + 1]), __int2float_rn(d[T::GPL - 1]));
-            }
-        }
+        for (int j = 1; j < RK::PPG; ++j) d += dj[j];
+        prod[g] = __fmul_rn(ssp[g * R], xsp[g]);
+        fdot[g] = __int2float_rn(d);
     }
-    __syncwarp();
-#pragma unroll
-    for (int u = 0; u < R::U; ++u) {
-        if (u < nu) {
-            const float4* row = reinterpret_cast<const float4*>(cs + (size_t)(u * 32 + r * 8) * PW);
-#pragma unroll
-            for (int i = 0; i < 4 * T::GPL; ++i) {
-                const float4 q = row[i];
-                acc = __fmaf_rn(q.x, q.y, acc);
-                acc = __fmaf_rn(q.z, q.w, acc);
-            }
-        }
-    }
-    return acc;
 }
 
 // ---------------------------------------------------------------------------------------------- attention part
@@ -556,7 +628,7 @@ __device__ __forceinline__ void attention_part(const MegaParams& p, uint8_t* sme
     }
     consumer_sync();
     pf.stop(tid, 10);
-    pf.mark(tid, 28, pf.trace_slot >= 0);
+    pf.mark(tid, 30, pf.trace_slot >= 0);
 
     // ---- scores for this part's keys: float dot_product_avx256 (x86_simd.cpp:1447-1468): 8 FMA chains, then 0 + l0 + ... + l7
     uint2* att_g = p.score_t + (size_t)qh * p.score_stride;
@@ -691,7 +763,7 @@ __device__ __forceinline__ void attention_part(const MegaParams& p, uint8_t* sme
             for (; i < rows; ++i) { const float w = wp[i]; if (fabsf(w) > 1e-15f) o = __fmaf_rn(vb[(size_t)i * DW], w, o); }
             // the chunk is consumed: refill its slot with chunk c + NCH
             if (DW > 32) asm volatile("bar.sync 2, %0;" :: "r"(DW) : "memory"); else __syncwarp(DW == 32 ? kFull : ((1u << DW) - 1u));
-            if (tid == 0 && c + NCH < n_chunks) { fence_proxy_async(); issue_v(c + NCH); }
+            if (tid == 0 && c + NCH < n_chunks) issue_v(c + NCH);      // the slot's reads have retired (their values fed the chain)
         }
         {   // the new token's row
             const float w = att[pos], v = v_s[d0 + tid];
@@ -701,7 +773,7 @@ __device__ __forceinline__ void attention_part(const MegaParams& p, uint8_t* sme
         st_tag(p.attnt + (size_t)qh * HS + d0 + tid, o, tag_out);
         if (tid == 0) {
             *vcount = vbase + (uint32_t)n_chunks;
-            if (pf.p && pf.trace_slot >= 0) pf.p[29] = gtimer();
+            if (pf.p && pf.trace_slot >= 0) pf.p[31] = gtimer();
         }
     }
     pf.stop(tid, 15);
@@ -710,8 +782,7 @@ __device__ __forceinline__ void attention_part(const MegaParams& p, uint8_t* sme
 // ---------------------------------------------------------------------------------------------- the kernel
 template <int QT, int GS, int HS>
 __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __grid_constant__ MegaParams p) {
-    using T = Traits<QT, GS>;
-    using R = Ring<QT, GS>;
+    using RK = Rk<QT, GS>;
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t* ring = smem + p.off_ring;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.off_bars);
@@ -726,6 +797,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
         for (int i = 0; i < p.n_vchunks; ++i) mbar_init(&vfull[i], 1);
         *issued = 0u;
         reinterpret_cast<uint32_t*>(smem + p.off_misc)[28] = 0u;
+        for (int i = 0; i < 2 * kConsumerWarps; ++i) reinterpret_cast<uint32_t*>(smem + p.off_tok + kConsumerWarps * 2 * 32 * 4)[i] = 0u;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -747,35 +819,27 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
 #pragma unroll 1
                 for (int pi = 0; pi < n_phases; ++pi) {
                     const PhaseShape ph = phase_shape(p, pi);
-                    const int t0 = (int)((long long)ph.n_tasks * blockIdx.x / gridDim.x);
-                    const int t1 = (int)((long long)ph.n_tasks * (blockIdx.x + 1) / gridDim.x);
-                    const int spt_tile = ceil_div(ph.nkb, R::U);
-                    const uint32_t task_bytes = (uint32_t)ph.tt * ph.nkb * T::UNIT_BYTES;     // one warp's tile(s)
+                    const RkPart pt = rk_part(ph.M, blockIdx.x, gridDim.x);
+                    const int n_stages = ceil_div(ph.K * RK::ES, kStageRowBytes) * ph.tt;      // per tile
+                    const uint8_t* src = ph.w + ph.off[blockIdx.x];                 // the stream is laid out in issue order
 #pragma unroll 1
-                    for (int r0 = t0; r0 < t1; r0 += kConsumerWarps) {
-                        const int nw = min(kConsumerWarps, t1 - r0);
-                        const uint8_t* round_base = ph.w + (size_t)r0 * task_bytes;
+                    for (int t = 0; t < pt.nt; ++t) {
+                        int lr0, R;
+                        rk_tile(pt, t, lr0, R);
+                        const uint32_t bytes = (uint32_t)RK::stage_bytes(R);
 #pragma unroll 1
-                        for (int tile = 0; tile < ph.tt; ++tile) {
-#pragma unroll 1
-                            for (int ks = 0; ks < spt_tile; ++ks) {
-                                const uint32_t bytes = (uint32_t)min(R::U, ph.nkb - ks * R::U) * T::UNIT_BYTES;
-                                const uint8_t* src = round_base + ((size_t)tile * ph.nkb + (size_t)ks * R::U) * T::UNIT_BYTES;
-#pragma unroll 1
-                                for (int w = 0; w < nw; ++w) {
-                                    if (window < (uint32_t)n_slots && sc >= window) {
-                                        mbar_wait_sleep(&full[wslot], wpar);
-                                        if (++wslot == (uint32_t)n_slots) { wslot = 0; wpar ^= 1u; }
-                                    }
-                                    mbar_wait_sleep(&empty[slot], par);
-                                    mbar_arrive_expect_tx(&full[slot], bytes);
-                                    bulk_g2s(ring + (size_t)slot * R::SLOT_BYTES, src, bytes, &full[slot]);
-                                    __threadfence_block();                      // the barrier is armed before the count says so
-                                    st_shared_volatile_u32(issued, ++sc);
-                                    src += task_bytes;
-                                    if (++slot == (uint32_t)n_slots) { slot = 0; par ^= 1u; }
-                                }
+                        for (int st = 0; st < n_stages; ++st) {
+                            if (window < (uint32_t)n_slots && sc >= window) {
+                                mbar_wait_sleep(&full[wslot], wpar);
+                                if (++wslot == (uint32_t)n_slots) { wslot = 0; wpar ^= 1u; }
                             }
+                            mbar_wait_sleep(&empty[slot], par);
+                            mbar_arrive_expect_tx(&full[slot], bytes);
+                            bulk_g2s(ring + (size_t)slot * RK::SLOT_BYTES, src, bytes, &full[slot]);
+                            __threadfence_block();                      // the barrier is armed before the count says so
+                            st_shared_volatile_u32(issued, ++sc);
+                            src += bytes;
+                            if (++slot == (uint32_t)n_slots) { slot = 0; par ^= 1u; }
                         }
                     }
                 }
@@ -789,10 +853,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
     float* xs = reinterpret_cast<float*>(smem + p.off_xs);
     float* xt = reinterpret_cast<float*>(smem + p.off_xt);
     float* misc = reinterpret_cast<float*>(smem + p.off_misc);
-    float* cs = reinterpret_cast<float*>(smem + p.off_chain) + (size_t)warp * (R::U * 32 * 2 * T::GPL);
     const uint4* xq4 = reinterpret_cast<const uint4*>(xq);
-    const int r = lane >> 3, l = lane & 7;
-
     const int n_attn_ctas = p.n_heads * p.cph;
     const bool attn_cta = (int)blockIdx.x < n_attn_ctas;
     const int my_head = blockIdx.x / p.cph, my_part = blockIdx.x % p.cph;
@@ -801,6 +862,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
     pf.p = p.prof ? p.prof + (size_t)blockIdx.x * 32 : nullptr;
     pf.t0 = pf.p ? gtimer() : 0ull;
     pf.trace_slot = -1;
+    pf.ev = nullptr;
 
     // sequence state at launch: written by the previous kernel on this stream.  Kept in shared memory, not registers:
     // the phase loop below is register-bound (168 per thread with 9 warps on 4 schedulers) and must not spill.
@@ -832,12 +894,15 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
             const uint32_t tag_in = (pk == 1) ? tl + 3u : (pk == 2) ? tl + 4u : (pk == 3) ? tl + 5u : tag_x_in;
             const float* gain = (pk == 0) ? L->att_norm : (pk == 2) ? L->ffn_norm : (pk == 4) ? p.out_norm : nullptr;
             const bool traced = (step == p.n_steps - 1) && (layer == p.n_layers / 2) && pk < 4;
-            pf.trace_slot = traced ? 20 + pk : -1;
+            pf.trace_slot = traced ? 22 + pk : -1;
+            pf.ev = (traced && p.evlog && (blockIdx.x == 7 || blockIdx.x == gridDim.x - 3)) ? p.evlog + (blockIdx.x == 7 ? 0 : 4096) : nullptr;
+            pf.log(lane, warp, 8, pk);          // build starts
             {
                 const int K = (pk == 3) ? p.hidden : p.dim;
-                build_activation<QT, GS>(xq, xs, xt, misc, in, tag_in, gain, K, ceil_div(K, kKBlockElems), (pk == 4 && blockIdx.x == 0) ? p.tap_norm : nullptr, tid, pf);
+                build_activation<QT, GS>(xq, xs, xt, misc, in, tag_in, gain, K, (pk == 4 && blockIdx.x == 0) ? p.tap_norm : nullptr, tid, pf);
             }
             pf.stop(tid, 1);
+            pf.log(lane, warp, 7, pk);          // drain starts
             const PhaseShape ph = phase_shape(p, pi);        // evaluated after the build: nothing of it lives across the build
             float best_v = -INFINITY;
             int best_i = 0x7fffffff;
@@ -845,53 +910,110 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
             uint2* out = (pk == 0) ? p.qkvt : (pk == 2) ? p.hdt : p.x1t;
             const uint32_t tag_out = tl + ((pk == 0) ? 1u : (pk == 1) ? 4u : (pk == 2) ? 5u : 6u);
             {
-                const int t0 = (int)((long long)ph.n_tasks * blockIdx.x / gridDim.x);
-                const int t1 = (int)((long long)ph.n_tasks * (blockIdx.x + 1) / gridDim.x);
-                const int spt_tile = ceil_div(ph.nkb, R::U), spt = ph.tt * spt_tile;
-                if (pf.p && traced && tid == kProfThread && pk >= 2) pf.p[28 + pk] = ld_shared_volatile_u32(issued) - sc;   // stages the producer is ahead
+                constexpr int BM = (kMaxPairs / RK::GPS > 4) ? 4 : kMaxPairs / RK::GPS;      // my stages per superblock (both sub-streams)
+                const RkPart pt = rk_part(ph.M, blockIdx.x, gridDim.x);
+                const int nkc = ceil_div(ph.K * RK::ES, kStageRowBytes);
+                const int nsb = rk_nsb(nkc, RK::GPS, ph.tt);
+                // token plumbing: inbox of warp w = tok_acc[w][2][32] floats; tok_wr/tok_rd[w] count tokens written / consumed
+                float* tok_acc = reinterpret_cast<float*>(smem + p.off_tok);
+                uint32_t* tok_wr = reinterpret_cast<uint32_t*>(smem + p.off_tok + kConsumerWarps * 2 * 32 * 4);
+                uint32_t* tok_rd = tok_wr + kConsumerWarps;
 #pragma unroll 1
-                for (int r0 = t0; r0 < t1; r0 += kConsumerWarps) {
-                    const int nw = min(kConsumerWarps, t1 - r0);
-                    if (warp < nw) {
-                        const int row = (r0 + warp) * 4 + r;
+                for (int t = 0; t < pt.nt; ++t) {
+                    int lr0, R;
+                    rk_tile(pt, t, lr0, R);
+                    const int row = pt.rb + lr0 + lane;
+                    const bool live = lane < R;
+                    float acc = 0.0f, acc2 = 0.0f;                             // acc2: the W3 row of the fused W1/W3 stream
+#pragma unroll 1
+                    for (int j = 0; j < nsb; ++j) {
+                        int k0, S;
+                        rk_superblock(nkc, nsb, j, k0, S);
+                        const int base = S >> 3, rem = S & 7;
+                        const int mine = base + (warp < rem ? 1 : 0);         // my K chunks in this superblock
+                        const int my_kc = k0 + warp * base + min(warp, rem);
+                        const int nh = S >= kConsumerWarps ? kConsumerWarps : S;     // warps that hold the token in this superblock
+                        const bool last = (j == nsb - 1) && (warp == nh - 1);
                         // residual input of this row (x1 += tmp, tensor.cpp:723): its word was validated by an earlier build
                         float x_old = 0.0f;
-                        if ((pk == 1 || pk == 3) && l == 0 && row < ph.M) x_old = __ldcg(reinterpret_cast<const float*>(p.x1t + row));
-                        float acc = 0.0f, acc_first = 0.0f;
-#pragma unroll 1
-                        for (int s = 0; s < spt; ++s) {
-                            const uint32_t idx = sc + (uint32_t)(s * nw + warp);
-                            const uint32_t slot = idx % (uint32_t)n_slots, k = idx / (uint32_t)n_slots;
-                            const int tile = s / spt_tile, ks = s - tile * spt_tile, kb = ks * R::U;
-                            const int nu = min(R::U, ph.nkb - kb);
-                            if (tile == 1 && ks == 0) { acc_first = acc; acc = 0.0f; }       // W1 tile done, W3 tile starts
-                            pf.stop(tid, 2 + pk);
-                            while ((int)(ld_shared_volatile_u32(issued) - idx) <= 0) { }      // fact 4 in the header
-                            mbar_wait(&full[slot], k & 1u);
-                            pf.stop(tid, 7);                                                  // waiting for weights = the stream is the limit
-                            acc = stage_chain<QT, GS>(ring + (size_t)slot * R::SLOT_BYTES, nu, xq4 + (size_t)kb * (T::KB_BYTES / 16),
-                                                      xs + kb * 8 * T::GPL, cs, lane, acc);
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(&empty[slot]);
-                        }
-                        if (l == 0 && row < ph.M) {
-                            float v;
-                            if (pk == 0 || pk == 4) v = acc;
-                            else if (pk == 2) v = swiglu_exact(acc_first, acc);
-                            else v = __fadd_rn(x_old, acc);
-                            if (pk == 4) {
-                                p.logits[row] = v;
-                                if (v > best_v || (v == best_v && row < best_i)) { best_v = v; best_i = row; }
-                            } else {
-                                st_tag(out + row, v, tag_out);
+                        if (last && (pk == 1 || pk == 3) && live) x_old = __ldcg(reinterpret_cast<const float*>(p.x1t + row));
+                        // ---- parallel part: pairs of my stages
+                        float prod[BM][RK::GPS], fdot[BM][RK::GPS];
+                        const uint32_t sb_slot = sc % (uint32_t)n_slots, sb_par = (sc / (uint32_t)n_slots) & 1u;
+#pragma unroll
+                        for (int q = 0; q < BM; ++q) {
+                            if (q < mine * ph.tt) {
+                                const int i = (ph.tt == 2) ? (q >> 1) : q, m = (ph.tt == 2) ? (q & 1) : 0;
+                                const uint32_t rel = (uint32_t)((i * kConsumerWarps + warp) * ph.tt + m);      // position in issue order
+                                uint32_t sl = sb_slot + rel, pr = sb_par;
+                                while (sl >= (uint32_t)n_slots) { sl -= n_slots; pr ^= 1u; }
+                                pf.log(lane, warp, 1, (int)rel);
+                                while ((int)(ld_shared_volatile_u32(issued) - (sc + rel)) <= 0) __nanosleep(40);      // fact 4 in the header
+                                mbar_wait(&full[sl], pr);
+                                pf.stop(tid, 7);                                                  // waiting for weights = the stream is the limit
+                                pf.log(lane, warp, 2, (int)rel);
+                                if (live) stage_pairs<QT, GS>(ring + (size_t)sl * RK::SLOT_BYTES, R, xq4 + (my_kc + i) * RK::PIECES, xs + (my_kc + i) * RK::GPS, lane, prod[q], fdot[q]);
+                                __syncwarp();
+                                if (lane == 0) mbar_arrive(&empty[sl]);
+                                pf.stop(tid, 2 + pk);
+                                pf.log(lane, warp, 3, (int)rel);
                             }
                         }
+                        sc += (uint32_t)(S * ph.tt);
+                        // ---- serial part: the chain token
+                        if (mine > 0) {
+                            pf.log(lane, warp, 4, t);
+                            if (!(j == 0 && warp == 0)) {
+                                // receive: the previous holder (warp - 1, or the last holder of the previous superblock) filled my inbox
+                                // and arrived on my barrier (the PTX producer/consumer pattern: st.shared; bar.arrive | bar.sync; ld.shared)
+                                asm volatile("bar.sync %0, 64;" :: "r"(3 + warp) : "memory");
+                                acc = tok_acc[(warp * 2) * 32 + lane];
+                                if (ph.tt == 2) acc2 = tok_acc[(warp * 2 + 1) * 32 + lane];
+                                __syncwarp();
+                                if (lane == 0) st_shared_volatile_u32(tok_rd + warp, ld_shared_volatile_u32(tok_rd + warp) + 1u);
+                            }
+                            pf.stop(tid, 20);
+                            pf.log(lane, warp, 5, t);
+#pragma unroll
+                            for (int q = 0; q < BM; ++q) {
+                                if (q < mine * ph.tt) {
+                                    if (ph.tt == 2 && (q & 1)) {
+#pragma unroll
+                                        for (int g = 0; g < RK::GPS; ++g) acc2 = __fmaf_rn(prod[q][g], fdot[q][g], acc2);
+                                    } else {
+#pragma unroll
+                                        for (int g = 0; g < RK::GPS; ++g) acc = __fmaf_rn(prod[q][g], fdot[q][g], acc);
+                                    }
+                                }
+                            }
+                            if (!last) {
+                                // send to the next holder
+                                const int nxt = (warp + 1 < nh) ? warp + 1 : 0;
+                                while (ld_shared_volatile_u32(tok_rd + nxt) != ld_shared_volatile_u32(tok_wr + nxt)) __nanosleep(20);     // its inbox is free
+                                tok_acc[(nxt * 2) * 32 + lane] = acc;
+                                if (ph.tt == 2) tok_acc[(nxt * 2 + 1) * 32 + lane] = acc2;
+                                if (lane == 0) st_shared_volatile_u32(tok_wr + nxt, ld_shared_volatile_u32(tok_wr + nxt) + 1u);
+                                asm volatile("bar.arrive %0, 64;" :: "r"(3 + nxt) : "memory");
+                            } else if (live) {
+                                float v;
+                                if (pk == 0 || pk == 4) v = acc;
+                                else if (pk == 2) v = swiglu_exact(acc, acc2);
+                                else v = __fadd_rn(x_old, acc);
+                                if (pk == 4) {
+                                    p.logits[row] = v;
+                                    if (v > best_v || (v == best_v && row < best_i)) { best_v = v; best_i = row; }
+                                } else {
+                                    st_tag(out + row, v, tag_out);
+                                }
+                            }
+                        }
+                        pf.stop(tid, 21);
+                        pf.log(lane, warp, 6, t);
                     }
-                    sc += (uint32_t)(nw * spt);
                 }
             }
             pf.stop(tid, 2 + pk);
-            if (pf.p && traced && lane == 0) atomicMax(pf.p + 24 + pk, gtimer());
+            if (pf.p && traced && lane == 0) atomicMax(pf.p + 26 + pk, gtimer());
             if (pk == 4) {
             // ---- argmax (sampler.cpp:36-46: first index of the strict maximum): per-CTA partial, exchanged as tagged words;
             //      every CTA reduces all partials, so every CTA knows the next token without another round trip

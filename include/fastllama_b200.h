@@ -122,7 +122,8 @@ void* fl_device_ptr(fl_engine* e, const char* name, int seq_slot);
  * out[cta*32 + k], k = 0 waiting for tagged input words (exchange latency + slowest producer), 1 activation rebuild tail
  * (quantise after the rmsnorm chain), 2 QKV, 3 Wo, 4 W1/W3, 5 W2, 6 classifier (weight-stream drains), 8 rebuild: products
  * + transpose, 9 rebuild: sum-of-squares chain, 10 attention: q/k/v fetch + RoPE + append, 11 QK^T, 12 score exchange,
- * 13 softmax, 14-17 PV (wait for V chunk, chain, issue next chunk, publish), 18 argmax exchange, 19 embedding row.
+ * 13 softmax, 15 PV chains, 18 argmax exchange, 19 embedding row, 7 waiting for weight stages (the stream is the limit),
+ * 20 waiting for the chain token, 21 chain + hand-off; 22-31 are absolute timestamps of one traced layer (profiles/trace_layer.py).
  * Needs FL_FLAG_PROFILE.  Returns the element count (32 * n_CTAs). */
 int  fl_profile_read(fl_engine* e, uint64_t* out, int cap, int reset);
 /* number of kernels this engine has launched (graph nodes count once per replay) */

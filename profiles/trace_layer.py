@@ -1,6 +1,6 @@
 """One exchange under the microscope: absolute globaltimer stamps of the middle layer of the last decode step, per CTA.
-slots: 20+pk = input of phase pk complete (tags valid), 24+pk = drain of phase pk finished, 28 = attention has q/k/v,
-29 = attention finished.  Prints, per phase, the skew of the producers and the latency from the LAST producer's finish to
+slots: 22+pk = input of phase pk complete (tags valid), 26+pk = drain of phase pk finished, 30 = attention has q/k/v,
+31 = attention finished.  Prints, per phase, the skew of the producers and the latency from the LAST producer's finish to
 each consumer's "input complete"."""
 import os, sys
 import numpy as np
@@ -20,8 +20,7 @@ eng.forward(np.array([5], np.int32), ctx - 2, want_logits=False)
 eng.profile_read(reset=True)
 eng.decode_async(steps); eng.sync()
 pr = eng.profile_read().astype(np.int64)
-t = pr[:, 20:30].astype(np.float64)
-print('stages ahead at W13 drain start:', np.bincount(pr[:, 30].clip(0, 40))[:30].tolist()); print('stages ahead at W2 drain start:', np.bincount(pr[:, 31].clip(0, 40))[:30].tolist())
+t = pr[:, 22:32].astype(np.float64)
 n_attn = spec.n_heads * 4
 t[t < 1] = np.nan
 base = t[:, 0].min()
