@@ -284,7 +284,7 @@ int enqueue_step(fl_engine* e, int slot, cudaStream_t st, int* n_kernels) {
         a.tap_qkv = (l == c.n_layers - 1) ? e->tap_qkv : nullptr;
         a.n_heads = c.n_heads; a.n_kv_heads = c.n_kv_heads; a.max_seq = c.max_seq_len;
         a.attn_scale = 1.0f / sqrtf((float)c.head_size);
-        a.v_dw = c.head_size / e->cph;
+        a.v_dw = c.head_size;          // the per-phase kernels keep natural V rows (the persistent kernel has its own blocked layout)
         rc = launch_attn(e, c.head_size, a, c.max_seq_len, st);
         if (rc) return rc;
         ++nk;
@@ -392,7 +392,7 @@ int setup_mega(fl_engine* e) {
     p.off_att = (int)off; off += al((size_t)c.max_seq_len * 4 + 64, 128);
     p.off_xs = (int)off; off += al((size_t)nkc_max * gps * 4, 128);
     p.off_vbars = (int)off; off += 128;
-    p.off_tok = (int)off; off += kConsumerWarps * 2 * 32 * 4 + 128;      // chain-token inboxes + their counters
+    p.off_pairs = (int)off; off += 2 * kPairGroups * 32 * 8;             // two pair buffers (consumers -> chain warp)
     // [activation image | transposed fp32 vector]: contiguous, because attention (which uses neither) turns the whole
     // range into its ring of V chunks
     const size_t xq_bytes = al((size_t)nkc_max * kStageRowBytes, 128), xt_bytes = al((size_t)c.dim * 4, 128);
@@ -411,6 +411,8 @@ int setup_mega(fl_engine* e) {
     if (n_slots < 4) return set_err(e, FL_ERR_UNSUPPORTED, "megakernel: not enough shared memory for the weight ring (%d slots)", n_slots);
     p.n_slots = n_slots;
     p.window = 99;
+    p.debug_skip = 0;
+    if (const char* w = getenv("FL_DEBUG_SKIP")) p.debug_skip = atoi(w);      // timing experiments only: results are garbage
     if (const char* w = getenv("FL_WINDOW")) { const int v = atoi(w); if (v >= 1) p.window = v; }      // tuning knob (profiles/)
     p.off_bars = (int)off; off += al((size_t)n_slots * 16, 128);
     p.off_ring = (int)off; off += (size_t)n_slots * slot_bytes;

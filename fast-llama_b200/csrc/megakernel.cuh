@@ -24,14 +24,16 @@
 // tiles of <= 32 rows, ONE LANE PER ROW.  A stage is 256 bytes of every row of a tile plus the rows' group scales, stored
 // piece-major so lane i's 16-byte piece sits next to lane i+1's (conflict-free LDS.128), and a CTA's stages lie in HBM in
 // exactly the order its producer issues them - its share of a phase is one contiguous byte range.
-// All 8 consumer warps work on the SAME tile: the K range is cut into 8 consecutive blocks, warp w computes, for its
-// block, every row's integer group dots (exact in any order) and scale products into registers.  The reference's FP32
-// chain over groups (quant_operators.cpp:274) is strictly sequential, so it travels as a TOKEN: warp 0 runs the chain over
-// its block, hands the 32 partial sums to warp 1 through shared memory, and so on; the last warp writes the rows.  The
-// expensive part (loads + dp4a) is fully parallel, the serial part is 4.5 cycles per group plus 7 hand-offs per tile,
-// and while the token of tile t travels the early warps already work on tile t+1.
-// (History, profiles/r01: a 4-rows-x-8-lanes layout that transposed (scale, dot) pairs through shared memory ran at
-// 1500 cycles per 8.7 KB stage per warp - slower than HBM; one warp per tile over the whole K was starved by ILP.)
+// The 8 consumer warps share the K chunks of a tile round-robin: for its chunk a warp computes, for every row (lane), the
+// integer group dots (exact in any order) and the scale products, and drops the (product, float(dot)) pairs into a
+// shared-memory pair buffer.  The reference's FP32 chain over groups (quant_operators.cpp:274) is strictly sequential, so
+// a tenth warp - the CHAIN WARP - owns it: per superblock of 32 groups it waits on a named barrier for the 8 consumers,
+// walks  acc = fma(product, dot, acc)  for its 32 rows (4.5 cycles per group), and after the last superblock applies the
+// epilogue (store / residual add / SwiGLU / argmax) and publishes the rows.  Producer -> consumers -> chain warp is a
+// three-stage pipeline: the expensive part (loads + dp4a) never waits for the serial part.
+// (History, profiles/r01: a 4-rows-x-8-lanes layout that transposed pairs per stage ran at 1500 cycles per 8.7 KB stage per
+// warp - slower than HBM; one warp per tile over the whole K starved on ILP; passing the chain as a token from warp to warp
+// cost 8 hand-offs of ~0.2 us per tile on the critical path.)
 //
 // Hardware facts that shape the code (all measured, see DESIGN.md "What the profiler taught us"):
 //   1. With ~227 KB of shared memory carved out there is practically no L1 left: every local-memory (stack) access and
@@ -49,9 +51,12 @@ namespace fl {
 
 constexpr int kConsumerWarps = 8;
 constexpr int kConsumerThreads = kConsumerWarps * 32;
-constexpr int kMegaThreads = kConsumerThreads + 32;
+constexpr int kMegaThreads = kConsumerThreads + 64;     // + TMA producer warp + chain warp
+constexpr int kPairGroups = 32;                          // groups (all sub-streams together) per superblock = per pair buffer
 constexpr int kTagsPerLayer = 8;
-constexpr int kProfThread = 31;       // keeps the profiling clock: last lane of warp 0 (in every GEMV round and in the PV group, not a chain lane)
+constexpr int kSerialWarp = kConsumerWarps - 1;   // runs the single-warp serial sections: the scheduler favours the highest warp id of a
+                                                  // sub-partition, and warp 7 shares its sub-partition only with warp 3 (not with the producer / chain warps)
+constexpr int kProfThread = kConsumerThreads - 1;  // keeps the profiling clock: last lane of the serial warp (in the PV group, not a chain lane)
 
 struct MegaLayer {
     const uint8_t* qkv;
@@ -86,10 +91,11 @@ struct MegaParams {
     int n_steps;
     int cph;                          // CTAs per head (1, 2 or 4)
     int n_slots;                      // ring stages
+    int debug_skip;                   // profiling experiments only (FL_DEBUG_SKIP): 1 = consumers release stages without computing
     int window;                       // max stages in flight (issued, not yet landed); >= n_slots: no limit
     uint32_t epoch;                   // tags of this launch are epoch + 1 ... epoch + n_steps * (n_layers + 1) * 8
     // dynamic shared memory carve-up (byte offsets)
-    int off_ring, off_xq, off_xs, off_xt, off_chain, off_att, off_misc, off_bars, off_vstage, off_vbars, off_tok;
+    int off_ring, off_xq, off_xs, off_xt, off_chain, off_att, off_misc, off_bars, off_vstage, off_vbars, off_pairs;
     int v_chunk_rows, n_vchunks;     // V ring of the attention part: n_vchunks chunks of v_chunk_rows rows x HS/cph floats
 };
 
@@ -161,13 +167,14 @@ __device__ __forceinline__ void st_relaxed_v4(uint4* p, uint4 v) {
 
 // per-CTA phase timing, only when MegaParams::prof is set; lives in registers.  Thread kProfThread keeps the clock.
 struct Prof {
-    unsigned long long* p; unsigned long long t0; int trace_slot;
-    unsigned long long* ev;           // event log of this CTA while the traced layer runs, else NULL
-    __device__ __forceinline__ void log(int lane, int warp, int type, int arg) {
-        if (ev && lane == 0) { const unsigned long long i = atomicAdd(ev, 1ull); if (i < 4095) ev[1 + i] = (gtimer() << 24) | ((unsigned long long)warp << 20) | ((unsigned long long)type << 12) | (unsigned long long)(arg & 0xfff); }
-    }   // trace_slot >= 0: the current build records when its input was complete
+    unsigned long long* p; unsigned long long t0; int trace_slot;   // trace_slot >= 0: the current build records when its input was complete
     __device__ __forceinline__ void stop(int tid, int cat) {
-        if (p && tid == kProfThread) { const unsigned long long t = gtimer(); atomicAdd(p + cat, t - t0); t0 = t; }
+        if (p && tid == kProfThread) { const unsigned long long t = (unsigned long long)clock64(); atomicAdd(p + cat, t - t0); t0 = t; }      // SM cycles: %globaltimer costs ~0.2 us a read
+    }
+    unsigned long long* ev;           // event log of this CTA while the traced layer runs, else NULL
+    unsigned int* evn;                // its event counter (shared memory: a global atomic with a return value costs a round trip)
+    __device__ __forceinline__ void log(int lane, int warp, int type, int arg) {
+        if (ev && lane == 0) { const unsigned int i = atomicAdd(evn, 1u); if (i < 4095u) ev[1 + i] = (gtimer() << 24) | ((unsigned long long)warp << 20) | ((unsigned long long)type << 12) | (unsigned long long)(arg & 0xfff); ev[0] = i + 1; }
     }
     // absolute timestamp of one event of the traced layer (slots 22..31): skew and latency of one exchange, see profiles/trace_layer.py
     __device__ __forceinline__ void mark(int tid, int slot, bool on) {
@@ -205,22 +212,13 @@ __host__ __device__ inline void rk_tile(const RkPart& pt, int t, int& lr0, int& 
     R = pt.nr * (t + 1) / pt.nt - lr0;
 }
 
-// K split of a tile: the nkc stages (K chunks) are cut into nsb superblocks; inside a superblock of S chunks warp w owns
-// the consecutive chunks [w*base + min(w, rem), ...) (base = S/8, rem = S%8, the first `rem` warps own one more) and keeps
-// their (scale product, dot) pairs in registers - at most kMaxPairs per lane, which bounds the superblock.
-constexpr int kMaxPairs = 24;
-__host__ __device__ inline int rk_bmax(int gps, int tt) {          // stages per warp per superblock, per sub-stream
-    int b = kMaxPairs / gps;
-    if (b > 4) b = 4;
-    if (tt == 2) b = b / 2;
-    return b < 1 ? 1 : b;
-}
-__host__ __device__ inline int rk_nsb(int nkc, int gps, int tt) { return (nkc + kConsumerWarps * rk_bmax(gps, tt) - 1) / (kConsumerWarps * rk_bmax(gps, tt)); }
+// A tile's K chunks are cut into nsb superblocks of at most kPairGroups / tt groups per sub-stream (one pair buffer).
+__host__ __device__ inline int rk_nsb(int nkc, int gps, int tt) { const int sk = kPairGroups / tt / gps; return (nkc + sk - 1) / sk; }
 __host__ __device__ inline void rk_superblock(int nkc, int nsb, int j, int& k0, int& S) { k0 = nkc * j / nsb; S = nkc * (j + 1) / nsb - k0; }
 
 // Pack rows [row_base, row_base + rows_src) of the logical matrix (M_total rows; `tt` sub-streams, this source is
 // sub-stream `m`: W1 = 0 / W3 = 1 of the fused W13 matrix) from the reference's row-major payload + scale table.
-// CTA stream order = issue order: [tile][superblock][i][warp][m]; stage = pieces p = 0..15 x R lanes x 16 B, then scales g x R.
+// CTA stream order = issue order: [tile][K chunk][m]; stage = pieces p = 0..15 x R lanes x 16 B, then scales g x R.
 template <int QT, int GS>
 __global__ void pack_rk_kernel(const uint8_t* __restrict__ raw, const float* __restrict__ scales, uint8_t* __restrict__ packed,
                                const unsigned long long* __restrict__ cta_off, int M_total, int K, int row_base, int rows_src, int tt, int m) {
@@ -228,22 +226,13 @@ __global__ void pack_rk_kernel(const uint8_t* __restrict__ raw, const float* __r
     const int c = blockIdx.x, G = gridDim.x;
     const RkPart pt = rk_part(M_total, c, G);
     const int kbytes = K * RK::ES, nkc = (kbytes + kStageRowBytes - 1) / kStageRowBytes, Gtot = K / GS;
-    const int nsb = rk_nsb(nkc, RK::GPS, tt);
     uint8_t* tile_base = packed + cta_off[c];
     for (int t = 0; t < pt.nt; ++t) {
         int lr0, R;
         rk_tile(pt, t, lr0, R);
         const int sb = RK::stage_bytes(R);
         for (int kc = blockIdx.y; kc < nkc; kc += gridDim.y) {
-            // which (superblock, warp, i) streams this K chunk
-            int j = 0, k0 = 0, S = 0;
-            for (; j < nsb; ++j) { rk_superblock(nkc, nsb, j, k0, S); if (kc < k0 + S) break; }
-            const int q = kc - k0, base = S >> 3, rem = S & 7;
-            int w, i;
-            if (q < rem * (base + 1)) { w = q / (base + 1); i = q - w * (base + 1); }
-            else { const int q2 = q - rem * (base + 1); w = rem + q2 / base; i = q2 - (w - rem) * base; }
-            const size_t stage_in_tile = (size_t)(k0 + i * kConsumerWarps + w) * tt + m;
-            uint8_t* st = tile_base + stage_in_tile * sb;
+            uint8_t* st = tile_base + ((size_t)kc * tt + m) * sb;
             const int n_items = R * RK::PIECES + R * RK::GPS;
             for (int idx = threadIdx.x; idx < n_items; idx += blockDim.x) {
                 if (idx < R * RK::PIECES) {
@@ -328,7 +317,7 @@ __device__ __forceinline__ void quant_store(uint8_t* xq, float* xs, const float 
 // simd::rmsnorm's sum of squares (x86_simd.cpp:941-962 via the __AVX2 typo at :1093): four FMA chains over x[4i+j], then
 // 0 + l0 + l1 + l2 + l3.  xt is the TRANSPOSED fp32 vector in shared memory: xt[j * n/4 + i] = x[4i + j], so lane j
 // streams its chain with 16-byte loads, double-buffered (5.4 cycles per dependent step on B200, profiles/r01: 2x the
-// natural-layout version).  Called by warp 0; returns the value in all its lanes.
+// natural-layout version).  Called by one warp; returns the value in all its lanes.
 __device__ __forceinline__ float sumsq_chain_t(const float* xt, int n, int lane) {
     float acc = 0.0f;
     if (lane < 4) {
@@ -474,7 +463,7 @@ __device__ __forceinline__ void build_activation(uint8_t* xq, float* xs, float* 
         if (gain) {
             consumer_sync();
             pf.stop(tid, 8);
-            if (warp == 0) {
+            if (warp == kSerialWarp) {
                 const float ss = sumsq_chain_t(xt, K, lane);
                 if (lane == 0) misc[0] = rms_scale(ss, K);
             }
@@ -500,11 +489,11 @@ __device__ __forceinline__ void build_activation(uint8_t* xq, float* xs, float* 
 
 // ---------------------------------------------------------------------------------------------- consumer GEMV phase
 // One stage = 256 bytes of each of the R rows of a tile.  Lane i owns row i: integer dots of its GPS groups (exact, any
-// order) and the scale products ws * xs, kept for the chain  acc = fma(ws * xs, float(dot), acc)  (quant_operators.cpp:274-275).
+// order) and the scale products ws * xs, stored as (product, float(dot)) pairs for the chain warp:
+// acc = fma(ws * xs, float(dot), acc)  (quant_operators.cpp:274-275).  pairs: [group][lane] float2 of this stage's groups.
 // xp / xsp: the activation image and scales of this K chunk (same for all lanes: broadcast loads).
 template <int QT, int GS>
-__device__ __forceinline__ void stage_pairs(const uint8_t* sp, int R, const uint4* xp, const float* xsp, int lane,
-                                            float (&prod)[Rk<QT, GS>::GPS], float (&fdot)[Rk<QT, GS>::GPS]) {
+__device__ __forceinline__ void stage_pairs(const uint8_t* sp, int R, const uint4* xp, const float* xsp, int lane, float2* pairs) {
     using RK = Rk<QT, GS>;
     const uint4* wp = reinterpret_cast<const uint4*>(sp) + lane;
     const float* ssp = reinterpret_cast<const float*>(sp + R * kStageRowBytes) + lane;
@@ -516,8 +505,7 @@ __device__ __forceinline__ void stage_pairs(const uint8_t* sp, int R, const uint
         int d = dj[0];
 #pragma unroll
         for (int j = 1; j < RK::PPG; ++j) d += dj[j];
-        prod[g] = __fmul_rn(ssp[g * R], xsp[g]);
-        fdot[g] = __int2float_rn(d);
+        pairs[g * 32 + lane] = make_float2(__fmul_rn(ssp[g * R], xsp[g]), __int2float_rn(d));
     }
 }
 
@@ -531,6 +519,49 @@ __device__ __forceinline__ void stage_pairs(const uint8_t* sp, int R, const uint
 // as register-double-buffered FP32 chains at ~5.5 cycles per dependent step.
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// rows [i, rows) of one V chunk for one head dim: o = fma(V[t], w_t, o) where |w_t| > 1e-15 (weighted_sum, tf_operators.cpp:325-350).
+// The chain runs on ONE warp, and a B200 sub-partition issues a warp's FP32/INT/LDS instruction every 2+ cycles, so the
+// instructions per row are what it costs (profiles/micro/pv_bench.cu: 14 cycles per row with one LDS per row).  Hence the V
+// cache keeps 4 consecutive positions of a head dim adjacent ([t/4][DW][4]): one LDS.128 brings 4 rows, the loads of the
+// next 16 rows are issued before the current 16 dependent FMAs, and blocks of 16 rows whose weights all pass the threshold
+// (slow == 0: virtually always) take an FFMA-only path.  vb points at this thread's dim inside the chunk: row r is vb[(r/4)*DW*4 + r%4].
+template <int DW>
+__device__ __forceinline__ float pv_rows(const float* vb, const float* wp, int i, int rows, uint32_t slow, float o) {
+    auto one = [&](int r) { const float w = wp[r]; if (fabsf(w) > 1e-15f) o = __fmaf_rn(vb[(r >> 2) * (DW * 4) + (r & 3)], w, o); };
+    for (; i < rows && (i & 15); ++i) one(i);
+    if (i + 16 <= rows) {
+        float4 v[4], w[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { v[u] = *reinterpret_cast<const float4*>(vb + ((i >> 2) + u) * (DW * 4)); w[u] = *reinterpret_cast<const float4*>(wp + i + 4 * u); }
+#pragma unroll 1
+        for (; i + 16 <= rows; i += 16) {
+            float4 nv[4], nw[4];
+            const int in = (i + 32 <= rows) ? i + 16 : i;              // prefetch the next block (or re-read this one on the last pass)
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { nv[u] = *reinterpret_cast<const float4*>(vb + ((in >> 2) + u) * (DW * 4)); nw[u] = *reinterpret_cast<const float4*>(wp + in + 4 * u); }
+            if (!((slow >> (i >> 4)) & 1u)) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    o = __fmaf_rn(v[u].x, w[u].x, o); o = __fmaf_rn(v[u].y, w[u].y, o);
+                    o = __fmaf_rn(v[u].z, w[u].z, o); o = __fmaf_rn(v[u].w, w[u].w, o);
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (fabsf(w[u].x) > 1e-15f) o = __fmaf_rn(v[u].x, w[u].x, o);
+                    if (fabsf(w[u].y) > 1e-15f) o = __fmaf_rn(v[u].y, w[u].y, o);
+                    if (fabsf(w[u].z) > 1e-15f) o = __fmaf_rn(v[u].z, w[u].z, o);
+                    if (fabsf(w[u].w) > 1e-15f) o = __fmaf_rn(v[u].w, w[u].w, o);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { v[u] = nv[u]; w[u] = nw[u]; }
+        }
+    }
+    for (; i < rows; ++i) one(i);
+    return o;
+}
+
 template <int HS>
 __device__ __forceinline__ void attention_part(const MegaParams& p, uint8_t* smem, int layer, int qh, int part, int pos, int bs,
                                                uint32_t tag_qkv, uint32_t tag_score, uint32_t tag_out, int tid, Prof& pf) {
@@ -543,6 +574,7 @@ __device__ __forceinline__ void attention_part(const MegaParams& p, uint8_t* sme
     float* v_s = k_s + HS;
     float* red = reinterpret_cast<float*>(smem + p.off_misc);
     uint32_t* vcount = reinterpret_cast<uint32_t*>(smem + p.off_misc) + 28;      // V chunks streamed so far by this CTA (ring position)
+    uint32_t* slowbits = reinterpret_cast<uint32_t*>(smem + p.off_misc) + 416;   // bit b of word w: 16-row block 32w + b holds a weight <= 1e-15
     float* v_stage = reinterpret_cast<float*>(smem + p.off_vstage);
     uint64_t* vfull = reinterpret_cast<uint64_t*>(smem + p.off_vbars);
     const int VR = p.v_chunk_rows, NCH = p.n_vchunks;
@@ -554,7 +586,7 @@ __device__ __forceinline__ void attention_part(const MegaParams& p, uint8_t* sme
     const int warp = tid >> 5, lane = tid & 31;
     const size_t cache_off = ((size_t)layer * p.n_kv_heads + kvh) * p.max_seq * HS;
     float* kc = p.k_cache + cache_off;
-    float* vc = p.v_cache + cache_off + (size_t)part * p.max_seq * DW;      // this part's column block: [max_seq][DW]
+    float* vc = p.v_cache + cache_off + (size_t)part * p.max_seq * DW;      // this part's column block: [max_seq / 4][DW][4 positions]
     const int d0 = part * DW;
 
     // ---- V ring: chunk c = cached rows [c*VR, min(pos, (c+1)*VR)) of the column block, one bulk copy each
@@ -563,11 +595,13 @@ __device__ __forceinline__ void attention_part(const MegaParams& p, uint8_t* sme
     auto issue_v = [&](int c) {                             // one thread
         const uint32_t gidx = vbase + (uint32_t)c;
         const uint32_t slot = gidx % (uint32_t)NCH;
-        const uint32_t bytes = (uint32_t)min(VR, pos - c * VR) * DW * 4;
+        const uint32_t bytes = (uint32_t)((min(VR, pos - c * VR) + 3) >> 2) * DW * 16;      // whole blocks of 4 positions
         mbar_arrive_expect_tx(&vfull[slot], bytes);
         bulk_g2s(v_stage + (size_t)slot * VR * DW, vc + (size_t)c * VR * DW, bytes, &vfull[slot]);
     };
-    if (tid == 0) {
+    if (tid < 32) slowbits[tid] = 0u;
+    const int pvt = tid - (kConsumerThreads - DW);          // index inside the PV group (the last DW consumer threads), < 0 for the others
+    if (pvt == 0) {
         fence_proxy_async();                                // the ring aliases memory the generic proxy wrote (activation image)
         for (int c = 0; c < min(NCH, n_chunks); ++c) issue_v(c);
     }
@@ -621,13 +655,14 @@ __device__ __forceinline__ void attention_part(const MegaParams& p, uint8_t* sme
         } else {
             v_s[2 * i] = x0; v_s[2 * i + 1] = x1;
             if (g == 0 && part == 0) {
-                float* vrow = p.v_cache + cache_off + ((size_t)((2 * i) / DW) * p.max_seq + pos) * DW + (2 * i) % DW;
-                *reinterpret_cast<float2*>(vrow) = make_float2(x0, x1);
+                float* vblk = p.v_cache + cache_off + (size_t)((2 * i) / DW) * p.max_seq * DW + ((size_t)(pos >> 2) * DW + (2 * i) % DW) * 4 + (pos & 3);
+                vblk[0] = x0; vblk[4] = x1;
             }
         }
     }
     consumer_sync();
     pf.stop(tid, 10);
+    pf.log(lane, warp, 16, 0);
     pf.mark(tid, 30, pf.trace_slot >= 0);
 
     // ---- scores for this part's keys: float dot_product_avx256 (x86_simd.cpp:1447-1468): 8 FMA chains, then 0 + l0 + ... + l7
@@ -680,6 +715,7 @@ __device__ __forceinline__ void attention_part(const MegaParams& p, uint8_t* sme
     }
     consumer_sync();
     pf.stop(tid, 12);
+    pf.log(lane, warp, 13, 0);
 
     // ---- softmax_sisd (tf_operators.cpp:176-186): max, expf(x - max), serial sum, divide
     float m = -INFINITY;
@@ -694,7 +730,7 @@ __device__ __forceinline__ void attention_part(const MegaParams& p, uint8_t* sme
     for (int t = tid; t < n; t += kConsumerThreads) att[t] = expf_exact(__fsub_rn(att[t], m));
     if (tid < 8) att[n + tid] = 0.0f;                      // the chains below read whole float4s
     consumer_sync();
-    if (tid == 0) {
+    if (tid == kSerialWarp * 32) {
         // one FP32 add chain in index order; loads run one batch ahead of the adds
         const float4* a4 = reinterpret_cast<const float4*>(att);
         const int nv = n >> 2;
@@ -713,70 +749,59 @@ __device__ __forceinline__ void attention_part(const MegaParams& p, uint8_t* sme
     }
     consumer_sync();
     const float sum = red[16];
-    for (int t = tid; t < n; t += kConsumerThreads) att[t] = __fdiv_rn(att[t], sum);
+    for (int t = tid; t < n; t += kConsumerThreads) {
+        const float w = __fdiv_rn(att[t], sum);
+        att[t] = w;
+        if (!(fabsf(w) > 1e-15f)) atomicOr(slowbits + (t >> 9), 1u << ((t >> 4) & 31));
+    }
     consumer_sync();
     pf.stop(tid, 13);
+    pf.log(lane, warp, 14, 0);
 
     // ---- weighted_sum (tf_operators.cpp:325-350): o = V[0]*w0; t >= 1: if |w_t| > 1e-15: o = fma(V[t], w_t, o) — one chain
-    // per head dim, run by the first DW threads without CTA-wide synchronisation; thread 0 refills the chunk ring.
-    if (tid < DW) {
+    // per head dim, run by the PV group without CTA-wide synchronisation; its first thread refills the chunk ring.
+    if (pvt >= 0) {
+        long long ck = clock64(), c_wait = 0, c_loop = 0, c_rest = 0;      // cycle split of the PV section (profiling)
         float o = 0.0f;
-        bool first = true;
+        uint32_t slot = vbase % (uint32_t)NCH, par = (vbase / (uint32_t)NCH) & 1u;
+        const float* wp = att;
 #pragma unroll 1
         for (int c = 0; c < n_chunks; ++c) {
-            const uint32_t gidx = vbase + (uint32_t)c;
-            const uint32_t slot = gidx % (uint32_t)NCH;
-            mbar_wait(&vfull[slot], (gidx / (uint32_t)NCH) & 1u);
-            const float* vb = v_stage + (size_t)slot * VR * DW + tid;
-            const int t0 = c * VR, rows = min(VR, pos - t0);
-            const float* wp = att + t0;
+            { const long long t = clock64(); c_rest += t - ck; ck = t; }
+            mbar_wait(&vfull[slot], par);
+            { const long long t = clock64(); c_wait += t - ck; ck = t; }
+            const float* vb = v_stage + (size_t)slot * VR * DW + pvt * 4;
+            const int rows = min(VR, pos - c * VR);
+            const uint32_t slow = (slowbits[(c * VR) >> 9] >> (((c * VR) >> 4) & 31));        // VR <= 64 rows: at most 4 blocks, inside one word
             int i = 0;
-            if (first) { o = __fmul_rn(vb[0], wp[0]); i = 1; first = false; }
-            // head of the chunk up to a multiple of 4 rows, then 8 rows per iteration with the loads one iteration ahead
-            for (; i < rows && (i & 3); ++i) { const float w = wp[i]; if (fabsf(w) > 1e-15f) o = __fmaf_rn(vb[(size_t)i * DW], w, o); }
-            if (i + 8 <= rows) {
-                float4 w0 = *reinterpret_cast<const float4*>(wp + i), w1 = *reinterpret_cast<const float4*>(wp + i + 4);
-                float v[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) v[u] = vb[(size_t)(i + u) * DW];
-#pragma unroll 1
-                for (; i + 8 <= rows; i += 8) {
-                    float4 nw0 = w0, nw1 = w1;
-                    float nv[8];
-                    const bool more = i + 16 <= rows;
-                    if (more) { nw0 = *reinterpret_cast<const float4*>(wp + i + 8); nw1 = *reinterpret_cast<const float4*>(wp + i + 12); }
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) nv[u] = more ? vb[(size_t)(i + 8 + u) * DW] : 0.0f;
-                    if (fabsf(w0.x) > 1e-15f) o = __fmaf_rn(v[0], w0.x, o);
-                    if (fabsf(w0.y) > 1e-15f) o = __fmaf_rn(v[1], w0.y, o);
-                    if (fabsf(w0.z) > 1e-15f) o = __fmaf_rn(v[2], w0.z, o);
-                    if (fabsf(w0.w) > 1e-15f) o = __fmaf_rn(v[3], w0.w, o);
-                    if (fabsf(w1.x) > 1e-15f) o = __fmaf_rn(v[4], w1.x, o);
-                    if (fabsf(w1.y) > 1e-15f) o = __fmaf_rn(v[5], w1.y, o);
-                    if (fabsf(w1.z) > 1e-15f) o = __fmaf_rn(v[6], w1.z, o);
-                    if (fabsf(w1.w) > 1e-15f) o = __fmaf_rn(v[7], w1.w, o);
-                    w0 = nw0; w1 = nw1;
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) v[u] = nv[u];
-                }
+            if (c == 0) { o = __fmul_rn(vb[0], wp[0]); i = 1; }          // row 0 of my dim
+            switch (DW) {
+                case 32: o = pv_rows<32>(vb, wp, i, rows, slow, o); break;
+                case 64: o = pv_rows<64>(vb, wp, i, rows, slow, o); break;
+                case 128: o = pv_rows<128>(vb, wp, i, rows, slow, o); break;
+                default: o = pv_rows<16>(vb, wp, i, rows, slow, o); break;
             }
-            for (; i < rows; ++i) { const float w = wp[i]; if (fabsf(w) > 1e-15f) o = __fmaf_rn(vb[(size_t)i * DW], w, o); }
+            wp += VR;
+            { const long long t = clock64(); c_loop += t - ck; ck = t; }
             // the chunk is consumed: refill its slot with chunk c + NCH
-            if (DW > 32) asm volatile("bar.sync 2, %0;" :: "r"(DW) : "memory"); else __syncwarp(DW == 32 ? kFull : ((1u << DW) - 1u));
-            if (tid == 0 && c + NCH < n_chunks) issue_v(c + NCH);      // the slot's reads have retired (their values fed the chain)
+            if (DW > 32) asm volatile("bar.sync 2, %0;" :: "r"(DW) : "memory"); else __syncwarp(DW == 32 ? kFull : (kFull << (32 - DW)));      // the PV group is the top DW lanes of its warp
+            if (pvt == 0 && c + NCH < n_chunks) issue_v(c + NCH);      // the slot's reads have retired (their values fed the chain)
+            if (++slot == (uint32_t)NCH) { slot = 0; par ^= 1u; }
         }
         {   // the new token's row
-            const float w = att[pos], v = v_s[d0 + tid];
-            if (first) o = __fmul_rn(v, w);
+            const float w = att[pos], v = v_s[d0 + pvt];
+            if (n_chunks == 0) o = __fmul_rn(v, w);
             else if (fabsf(w) > 1e-15f) o = __fmaf_rn(v, w, o);
         }
-        st_tag(p.attnt + (size_t)qh * HS + d0 + tid, o, tag_out);
-        if (tid == 0) {
+        st_tag(p.attnt + (size_t)qh * HS + d0 + pvt, o, tag_out);
+        if (pf.p && tid == kProfThread) { c_rest += clock64() - ck; atomicAdd(pf.p + 14, (unsigned long long)c_wait); atomicAdd(pf.p + 16, (unsigned long long)c_loop); atomicAdd(pf.p + 17, (unsigned long long)c_rest); }
+        if (pvt == 0) {
             *vcount = vbase + (uint32_t)n_chunks;
             if (pf.p && pf.trace_slot >= 0) pf.p[31] = gtimer();
         }
     }
     pf.stop(tid, 15);
+    if (!(p.debug_skip & 4)) consumer_sync();     // the other warps start polling for the next phase only now: their strong loads share the LSU with the PV warp's shared-memory loads
 }
 
 // ---------------------------------------------------------------------------------------------- the kernel
@@ -797,7 +822,9 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
         for (int i = 0; i < p.n_vchunks; ++i) mbar_init(&vfull[i], 1);
         *issued = 0u;
         reinterpret_cast<uint32_t*>(smem + p.off_misc)[28] = 0u;
-        for (int i = 0; i < 2 * kConsumerWarps; ++i) reinterpret_cast<uint32_t*>(smem + p.off_tok + kConsumerWarps * 2 * 32 * 4)[i] = 0u;
+        reinterpret_cast<uint32_t*>(smem + p.off_misc)[24] = 0u;      // pair buffer 0 / 1: times released by the chain warp
+        reinterpret_cast<uint32_t*>(smem + p.off_misc)[25] = 0u;
+        reinterpret_cast<uint32_t*>(smem + p.off_misc)[31] = 0u;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -848,6 +875,103 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
         return;
     }
 
+    float2* pairbuf = reinterpret_cast<float2*>(smem + p.off_pairs);            // [2 buffers][kPairGroups][32 lanes]
+    uint32_t* freed = reinterpret_cast<uint32_t*>(smem + p.off_misc) + 24;      // [2] releases of each pair buffer (chain warp -> consumers)
+
+    if (warp == kConsumerWarps + 1) {
+        // ================= chain warp =================
+        // Follows the consumers' schedule superblock by superblock; lane i owns row i of the current tile.
+        uint32_t sbseq = 0;                                  // superblocks so far (buffer = sbseq & 1)
+        Prof pf;
+        pf.p = p.prof ? p.prof + (size_t)blockIdx.x * 32 : nullptr; pf.t0 = 0ull; pf.trace_slot = -1; pf.ev = nullptr;
+        pf.evn = reinterpret_cast<unsigned int*>(smem + p.off_misc) + 31;
+#pragma unroll 1
+        for (int step = 0; step < p.n_steps; ++step) {
+            const uint32_t tbase = p.epoch + 1u + (uint32_t)step * (uint32_t)(p.n_layers + 1) * kTagsPerLayer;
+#pragma unroll 1
+            for (int pi = 0; pi < n_phases; ++pi) {
+                const PhaseShape ph = phase_shape(p, pi);
+                const int layer = pi >> 2, pk = (pi == n_phases - 1) ? 4 : (pi & 3);
+                pf.ev = ((step == p.n_steps - 1) && (layer == p.n_layers / 2) && pk < 4 && p.evlog && (p.debug_skip & 16) && (blockIdx.x == 7 || blockIdx.x == gridDim.x - 3)) ? p.evlog + (blockIdx.x == 7 ? 0 : 4096) : nullptr;
+                const uint32_t tl = tbase + (uint32_t)layer * kTagsPerLayer;
+                uint2* out = (pk == 0) ? p.qkvt : (pk == 2) ? p.hdt : p.x1t;
+                const uint32_t tag_out = tl + ((pk == 0) ? 1u : (pk == 1) ? 4u : (pk == 2) ? 5u : 6u);
+                const RkPart pt = rk_part(ph.M, blockIdx.x, gridDim.x);
+                const int nkc = ceil_div(ph.K * RK::ES, kStageRowBytes);
+                const int nsb = rk_nsb(nkc, RK::GPS, ph.tt);
+                const int gstride = (kPairGroups / ph.tt) * 32;          // float2s per sub-stream in a pair buffer
+                float best_v = -INFINITY;
+                int best_i = 0x7fffffff;
+#pragma unroll 1
+                for (int t = 0; t < pt.nt; ++t) {
+                    int lr0, R;
+                    rk_tile(pt, t, lr0, R);
+                    const int row = pt.rb + lr0 + lane;
+                    const bool live = lane < R;
+                    // residual input of this row (x1 += tmp, tensor.cpp:723): its word was validated by the consumers' earlier build
+                    float x_old = 0.0f;
+                    if ((pk == 1 || pk == 3) && live) x_old = __ldcg(reinterpret_cast<const float*>(p.x1t + row));
+                    float acc = 0.0f, acc2 = 0.0f;                     // acc2: the W3 row of the fused W1/W3 stream
+#pragma unroll 1
+                    for (int j = 0; j < nsb; ++j) {
+                        int k0, S;
+                        rk_superblock(nkc, nsb, j, k0, S);
+                        const int ng = S * RK::GPS;
+                        const uint32_t buf = sbseq & 1u;
+                        pf.log(lane, 9, 4, j);
+                        asm volatile("bar.sync %0, %1;" :: "r"(3 + (int)buf), "n"(kConsumerThreads + 32) : "memory");     // the 8 consumers have arrived
+                        pf.log(lane, 9, 5, j);
+                        const float2* pb = pairbuf + (size_t)buf * kPairGroups * 32 + lane;
+                        // the chain: loads run a batch ahead of the dependent FMAs
+                        int g = 0;
+#pragma unroll 1
+                        for (; g + 8 <= ng; g += 8) {
+                            float2 a[8], b[8];
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) { a[u] = pb[(g + u) * 32]; if (ph.tt == 2) b[u] = pb[gstride + (g + u) * 32]; }
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) { acc = __fmaf_rn(a[u].x, a[u].y, acc); if (ph.tt == 2) acc2 = __fmaf_rn(b[u].x, b[u].y, acc2); }
+                        }
+                        for (; g < ng; ++g) {
+                            const float2 a = pb[g * 32];
+                            acc = __fmaf_rn(a.x, a.y, acc);
+                            if (ph.tt == 2) { const float2 b = pb[gstride + g * 32]; acc2 = __fmaf_rn(b.x, b.y, acc2); }
+                        }
+                        __syncwarp();
+                        if (lane == 0) st_shared_volatile_u32(freed + buf, (sbseq >> 1) + 1u);        // buffer released
+                        ++sbseq;
+                    }
+                    if (live) {
+                        float v;
+                        if (pk == 0 || pk == 4) v = acc;
+                        else if (pk == 2) v = swiglu_exact(acc, acc2);
+                        else v = __fadd_rn(x_old, acc);
+                        if (pk == 4) {
+                            p.logits[row] = v;
+                            if (v > best_v || (v == best_v && row < best_i)) { best_v = v; best_i = row; }
+                        } else {
+                            st_tag(out + row, v, tag_out);
+                        }
+                    }
+                    pf.log(lane, 9, 6, t);
+                }
+                if (pk == 4) {
+                    // per-CTA argmax partial (sampler.cpp:36-46: first index of the strict maximum)
+                    const uint32_t tag_am = tbase + (uint32_t)p.n_layers * kTagsPerLayer + 1u;
+                    float bv = best_v; int bi = best_i;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const float ov = __shfl_xor_sync(kFull, bv, o);
+                        const int oi = __shfl_xor_sync(kFull, bi, o);
+                        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+                    }
+                    if (lane == 0) st_relaxed_v4(p.am + blockIdx.x, make_uint4(__float_as_uint(bv), tag_am, (uint32_t)bi, tag_am));
+                }
+            }
+        }
+        return;
+    }
+
     // ================= consumers =================
     uint8_t* xq = smem + p.off_xq;
     float* xs = reinterpret_cast<float*>(smem + p.off_xs);
@@ -857,12 +981,13 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
     const int n_attn_ctas = p.n_heads * p.cph;
     const bool attn_cta = (int)blockIdx.x < n_attn_ctas;
     const int my_head = blockIdx.x / p.cph, my_part = blockIdx.x % p.cph;
-    uint32_t sc = 0;
+    uint32_t sc = 0, cseq = 0, sbseq = 0;      // stages / K chunks / superblocks so far
     Prof pf;
     pf.p = p.prof ? p.prof + (size_t)blockIdx.x * 32 : nullptr;
-    pf.t0 = pf.p ? gtimer() : 0ull;
+    pf.t0 = pf.p ? (unsigned long long)clock64() : 0ull;
     pf.trace_slot = -1;
     pf.ev = nullptr;
+    pf.evn = reinterpret_cast<unsigned int*>(smem + p.off_misc) + 31;
 
     // sequence state at launch: written by the previous kernel on this stream.  Kept in shared memory, not registers:
     // the phase loop below is register-bound (168 per thread with 9 warps on 4 schedulers) and must not spill.
@@ -895,7 +1020,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
             const float* gain = (pk == 0) ? L->att_norm : (pk == 2) ? L->ffn_norm : (pk == 4) ? p.out_norm : nullptr;
             const bool traced = (step == p.n_steps - 1) && (layer == p.n_layers / 2) && pk < 4;
             pf.trace_slot = traced ? 22 + pk : -1;
-            pf.ev = (traced && p.evlog && (blockIdx.x == 7 || blockIdx.x == gridDim.x - 3)) ? p.evlog + (blockIdx.x == 7 ? 0 : 4096) : nullptr;
+            pf.ev = (traced && p.evlog && (p.debug_skip & 16) && (blockIdx.x == 7 || blockIdx.x == gridDim.x - 3)) ? p.evlog + (blockIdx.x == 7 ? 0 : 4096) : nullptr;
             pf.log(lane, warp, 8, pk);          // build starts
             {
                 const int K = (pk == 3) ? p.hidden : p.dim;
@@ -904,145 +1029,76 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
             pf.stop(tid, 1);
             pf.log(lane, warp, 7, pk);          // drain starts
             const PhaseShape ph = phase_shape(p, pi);        // evaluated after the build: nothing of it lives across the build
-            float best_v = -INFINITY;
-            int best_i = 0x7fffffff;
             // ---- drain this CTA's stages of the phase
             uint2* out = (pk == 0) ? p.qkvt : (pk == 2) ? p.hdt : p.x1t;
             const uint32_t tag_out = tl + ((pk == 0) ? 1u : (pk == 1) ? 4u : (pk == 2) ? 5u : 6u);
             {
-                constexpr int BM = (kMaxPairs / RK::GPS > 4) ? 4 : kMaxPairs / RK::GPS;      // my stages per superblock (both sub-streams)
                 const RkPart pt = rk_part(ph.M, blockIdx.x, gridDim.x);
                 const int nkc = ceil_div(ph.K * RK::ES, kStageRowBytes);
                 const int nsb = rk_nsb(nkc, RK::GPS, ph.tt);
-                // token plumbing: inbox of warp w = tok_acc[w][2][32] floats; tok_wr/tok_rd[w] count tokens written / consumed
-                float* tok_acc = reinterpret_cast<float*>(smem + p.off_tok);
-                uint32_t* tok_wr = reinterpret_cast<uint32_t*>(smem + p.off_tok + kConsumerWarps * 2 * 32 * 4);
-                uint32_t* tok_rd = tok_wr + kConsumerWarps;
+                const int gstride = (kPairGroups / ph.tt) * 32;          // float2s per sub-stream in a pair buffer
+                if (pf.p && tid == kProfThread) atomicAdd(pf.p + 20, (unsigned long long)(ld_shared_volatile_u32(issued) - sc));   // stages the producer is ahead at drain start
 #pragma unroll 1
                 for (int t = 0; t < pt.nt; ++t) {
                     int lr0, R;
                     rk_tile(pt, t, lr0, R);
-                    const int row = pt.rb + lr0 + lane;
                     const bool live = lane < R;
-                    float acc = 0.0f, acc2 = 0.0f;                             // acc2: the W3 row of the fused W1/W3 stream
 #pragma unroll 1
                     for (int j = 0; j < nsb; ++j) {
                         int k0, S;
                         rk_superblock(nkc, nsb, j, k0, S);
-                        const int base = S >> 3, rem = S & 7;
-                        const int mine = base + (warp < rem ? 1 : 0);         // my K chunks in this superblock
-                        const int my_kc = k0 + warp * base + min(warp, rem);
-                        const int nh = S >= kConsumerWarps ? kConsumerWarps : S;     // warps that hold the token in this superblock
-                        const bool last = (j == nsb - 1) && (warp == nh - 1);
-                        // residual input of this row (x1 += tmp, tensor.cpp:723): its word was validated by an earlier build
-                        float x_old = 0.0f;
-                        if (last && (pk == 1 || pk == 3) && live) x_old = __ldcg(reinterpret_cast<const float*>(p.x1t + row));
-                        // ---- parallel part: pairs of my stages
-                        float prod[BM][RK::GPS], fdot[BM][RK::GPS];
-                        const uint32_t sb_slot = sc % (uint32_t)n_slots, sb_par = (sc / (uint32_t)n_slots) & 1u;
-#pragma unroll
-                        for (int q = 0; q < BM; ++q) {
-                            if (q < mine * ph.tt) {
-                                const int i = (ph.tt == 2) ? (q >> 1) : q, m = (ph.tt == 2) ? (q & 1) : 0;
-                                const uint32_t rel = (uint32_t)((i * kConsumerWarps + warp) * ph.tt + m);      // position in issue order
-                                uint32_t sl = sb_slot + rel, pr = sb_par;
-                                while (sl >= (uint32_t)n_slots) { sl -= n_slots; pr ^= 1u; }
-                                pf.log(lane, warp, 1, (int)rel);
-                                while ((int)(ld_shared_volatile_u32(issued) - (sc + rel)) <= 0) __nanosleep(40);      // fact 4 in the header
+                        const uint32_t buf = sbseq & 1u;
+                        // the chain warp has released this pair buffer (it is two superblocks behind at worst)
+                        while ((int)(ld_shared_volatile_u32(freed + buf) - (sbseq >> 1)) < 0) __nanosleep(20);
+                        pf.log(lane, warp, 10, j);
+                        float2* pb = pairbuf + (size_t)buf * kPairGroups * 32;
+                        // my K chunks of this superblock: chunks are dealt round-robin over the warps, continuing across superblocks
+                        uint32_t q = ((uint32_t)warp - cseq) & 7u;
+                        uint32_t rel = q * (uint32_t)ph.tt;                              // position in issue order, relative to sc
+                        uint32_t sl = (sc + rel) % (uint32_t)n_slots, pr = ((sc + rel) / (uint32_t)n_slots) & 1u;
+#pragma unroll 1
+                        for (; q < (uint32_t)S; q += 8) {
+#pragma unroll 1
+                            for (int m = 0; m < ph.tt; ++m) {
+                                pf.log(lane, warp, 1, (int)rel + m);
+                                while ((int)(ld_shared_volatile_u32(issued) - (sc + rel + (uint32_t)m)) <= 0) __nanosleep(40);      // fact 4 in the header
                                 mbar_wait(&full[sl], pr);
                                 pf.stop(tid, 7);                                                  // waiting for weights = the stream is the limit
-                                pf.log(lane, warp, 2, (int)rel);
-                                if (live) stage_pairs<QT, GS>(ring + (size_t)sl * RK::SLOT_BYTES, R, xq4 + (my_kc + i) * RK::PIECES, xs + (my_kc + i) * RK::GPS, lane, prod[q], fdot[q]);
+                                pf.log(lane, warp, 2, (int)rel + m);
+                                if (live && !(p.debug_skip & 1)) stage_pairs<QT, GS>(ring + (size_t)sl * RK::SLOT_BYTES, R, xq4 + (k0 + (int)q) * RK::PIECES, xs + (k0 + (int)q) * RK::GPS, lane,
+                                                             pb + m * gstride + (int)q * RK::GPS * 32);
                                 __syncwarp();
                                 if (lane == 0) mbar_arrive(&empty[sl]);
                                 pf.stop(tid, 2 + pk);
-                                pf.log(lane, warp, 3, (int)rel);
+                                pf.log(lane, warp, 3, (int)rel + m);
+                                if (++sl == (uint32_t)n_slots) { sl = 0; pr ^= 1u; }
                             }
+                            rel += 8u * (uint32_t)ph.tt;
+                            sl += (8u - 1u) * (uint32_t)ph.tt;
+                            while (sl >= (uint32_t)n_slots) { sl -= n_slots; pr ^= 1u; }
                         }
                         sc += (uint32_t)(S * ph.tt);
-                        // ---- serial part: the chain token
-                        if (mine > 0) {
-                            pf.log(lane, warp, 4, t);
-                            if (!(j == 0 && warp == 0)) {
-                                // receive: the previous holder (warp - 1, or the last holder of the previous superblock) filled my inbox
-                                // and arrived on my barrier (the PTX producer/consumer pattern: st.shared; bar.arrive | bar.sync; ld.shared)
-                                asm volatile("bar.sync %0, 64;" :: "r"(3 + warp) : "memory");
-                                acc = tok_acc[(warp * 2) * 32 + lane];
-                                if (ph.tt == 2) acc2 = tok_acc[(warp * 2 + 1) * 32 + lane];
-                                __syncwarp();
-                                if (lane == 0) st_shared_volatile_u32(tok_rd + warp, ld_shared_volatile_u32(tok_rd + warp) + 1u);
-                            }
-                            pf.stop(tid, 20);
-                            pf.log(lane, warp, 5, t);
-#pragma unroll
-                            for (int q = 0; q < BM; ++q) {
-                                if (q < mine * ph.tt) {
-                                    if (ph.tt == 2 && (q & 1)) {
-#pragma unroll
-                                        for (int g = 0; g < RK::GPS; ++g) acc2 = __fmaf_rn(prod[q][g], fdot[q][g], acc2);
-                                    } else {
-#pragma unroll
-                                        for (int g = 0; g < RK::GPS; ++g) acc = __fmaf_rn(prod[q][g], fdot[q][g], acc);
-                                    }
-                                }
-                            }
-                            if (!last) {
-                                // send to the next holder
-                                const int nxt = (warp + 1 < nh) ? warp + 1 : 0;
-                                while (ld_shared_volatile_u32(tok_rd + nxt) != ld_shared_volatile_u32(tok_wr + nxt)) __nanosleep(20);     // its inbox is free
-                                tok_acc[(nxt * 2) * 32 + lane] = acc;
-                                if (ph.tt == 2) tok_acc[(nxt * 2 + 1) * 32 + lane] = acc2;
-                                if (lane == 0) st_shared_volatile_u32(tok_wr + nxt, ld_shared_volatile_u32(tok_wr + nxt) + 1u);
-                                asm volatile("bar.arrive %0, 64;" :: "r"(3 + nxt) : "memory");
-                            } else if (live) {
-                                float v;
-                                if (pk == 0 || pk == 4) v = acc;
-                                else if (pk == 2) v = swiglu_exact(acc, acc2);
-                                else v = __fadd_rn(x_old, acc);
-                                if (pk == 4) {
-                                    p.logits[row] = v;
-                                    if (v > best_v || (v == best_v && row < best_i)) { best_v = v; best_i = row; }
-                                } else {
-                                    st_tag(out + row, v, tag_out);
-                                }
-                            }
-                        }
-                        pf.stop(tid, 21);
-                        pf.log(lane, warp, 6, t);
+                        cseq += (uint32_t)S;
+                        ++sbseq;
+                        asm volatile("bar.arrive %0, %1;" :: "r"(3 + (int)buf), "n"(kConsumerThreads + 32) : "memory");     // my pairs of this superblock are in the buffer
                     }
                 }
             }
             pf.stop(tid, 2 + pk);
             if (pf.p && traced && lane == 0) atomicMax(pf.p + 26 + pk, gtimer());
             if (pk == 4) {
-            // ---- argmax (sampler.cpp:36-46: first index of the strict maximum): per-CTA partial, exchanged as tagged words;
-            //      every CTA reduces all partials, so every CTA knows the next token without another round trip
-            {
+                // ---- argmax (sampler.cpp:36-46): the chain warps published one partial per CTA as tagged words; every CTA
+                //      reduces all of them, so every CTA knows the next token without another round trip
                 const uint32_t tag_am = tbase + (uint32_t)p.n_layers * kTagsPerLayer + 1u;
-                float bv = best_v; int bi = best_i;
-    #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const float ov = __shfl_xor_sync(kFull, bv, o);
-                    const int oi = __shfl_xor_sync(kFull, bi, o);
-                    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-                }
-                float* sv = misc + 8; int* si = reinterpret_cast<int*>(misc + 16);
-                if (lane == 0) { sv[warp] = bv; si[warp] = bi; }
-                consumer_sync();
                 if (warp == 0) {
-                    if (lane == 0) {
-                        for (int w = 1; w < kConsumerWarps; ++w)
-                            if (sv[w] > bv || (sv[w] == bv && si[w] < bi)) { bv = sv[w]; bi = si[w]; }
-                        st_relaxed_v4(p.am + blockIdx.x, make_uint4(__float_as_uint(bv), tag_am, (uint32_t)bi, tag_am));
-                    }
-                    bv = -INFINITY; bi = 0x7fffffff;
+                    float bv = -INFINITY; int bi = 0x7fffffff;
                     for (int i = lane; i < (int)gridDim.x; i += 32) {
                         uint4 w = ld_relaxed_v4(p.am + i);
-                        while (w.y != tag_am || w.w != tag_am) w = ld_relaxed_v4(p.am + i);
+                        while (w.y != tag_am || w.w != tag_am) { __nanosleep(100); w = ld_relaxed_v4(p.am + i); }
                         const float v = __uint_as_float(w.x); const int ix = (int)w.z;
                         if (v > bv || (v == bv && ix < bi)) { bv = v; bi = ix; }
                     }
-    #pragma unroll
+#pragma unroll
                     for (int o = 16; o > 0; o >>= 1) {
                         const float ov = __shfl_xor_sync(kFull, bv, o);
                         const int oi = __shfl_xor_sync(kFull, bi, o);
@@ -1063,7 +1119,6 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
                     }
                 }
                 consumer_sync();
-            }
             }
             if (pk == 0 && attn_cta) {
                 // ---- attention (transformer.cpp:136, :397-455)

@@ -118,7 +118,7 @@ int   fl_sync(fl_engine* e);
 /* device addresses of per-slot state for zero-copy consumers on the engine stream (e.g. an NCCL all-gather of the
  * sampled token): name in {"token","pos","argmax","out_tokens","logits"}; NULL if unknown. */
 void* fl_device_ptr(fl_engine* e, const char* name, int seq_slot);
-/* per-CTA nanoseconds spent per category by the persistent decode kernel since the last reset:
+/* per-CTA SM cycles spent per category by the persistent decode kernel since the last reset:
  * out[cta*32 + k], k = 0 waiting for tagged input words (exchange latency + slowest producer), 1 activation rebuild tail
  * (quantise after the rmsnorm chain), 2 QKV, 3 Wo, 4 W1/W3, 5 W2, 6 classifier (weight-stream drains), 8 rebuild: products
  * + transpose, 9 rebuild: sum-of-squares chain, 10 attention: q/k/v fetch + RoPE + append, 11 QK^T, 12 score exchange,

@@ -221,6 +221,7 @@ struct StreamArgs {
     uint32_t pf_chunk;
     int touch;                              // consumers read the slot through shared memory
     int window;                             // max stages in flight (issued, not yet landed); >= n_slots: unlimited
+    int fence;                              // 1: __threadfence_block + volatile issue counter after every stage (as the decode kernel did), 2: counter only
 };
 __global__ void __launch_bounds__(kThreads, 1) stream_kernel(StreamArgs a, unsigned long long* ctr, unsigned long long* out_ns, float* sink) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -256,6 +257,8 @@ __global__ void __launch_bounds__(kThreads, 1) stream_kernel(StreamArgs a, unsig
                 while (!mbar_try(&empty[slot], par)) { __nanosleep(20); }
                 mbar_arrive_expect_tx(&full[slot], a.slot_bytes);
                 bulk_g2s(ring + (size_t)slot * a.slot_bytes, src + off, a.slot_bytes, &full[slot]);
+                if (a.fence == 1) __threadfence_block();
+                if (a.fence) *reinterpret_cast<volatile uint32_t*>(smem + 1016) = idx + 1;
                 off += a.slot_bytes; if (off >= region) off = 0;
                 if (lead > 0) --lead; else { pf_off = off; }
                 if (++slot == (uint32_t)a.n_slots) { slot = 0; par ^= 1u; }
@@ -363,20 +366,18 @@ int main(int argc, char** argv) {
     if (has('D')) {
         float* sink; CK(cudaMalloc(&sink, 64));
         const uint32_t slot = 8704;
-        struct Case { int n_slots; uint32_t phase_kb; uint32_t stall_ns; uint32_t ahead_kb; int touch; int window; };
+        struct Case { int n_slots; uint32_t phase_kb; uint32_t stall_ns; uint32_t ahead_kb; int touch; int window; int fence; };
         std::vector<Case> cases = {
-            {16, 306, 0, 0, 0, 99}, {24, 306, 0, 0, 0, 99}, {24, 306, 0, 0, 1, 99}, {24, 306, 0, 256, 0, 99},
-            {24, 306, 4000, 0, 0, 99}, {24, 306, 8000, 0, 0, 99}, {24, 306, 8000, 128, 0, 99}, {24, 306, 8000, 256, 0, 99}, {24, 306, 8000, 512, 0, 99}, {24, 306, 8000, 256, 1, 99},
-            {24, 306, 16000, 0, 0, 99}, {24, 306, 16000, 256, 0, 99}, {24, 306, 16000, 512, 0, 99}, {24, 306, 16000, 1024, 0, 99},
-            {24, 102, 6000, 0, 0, 99}, {24, 102, 6000, 256, 0, 99}, {24, 102, 6000, 512, 0, 99},
-            {16, 306, 8000, 0, 0, 99}, {16, 306, 8000, 256, 0, 99}, {16, 306, 8000, 512, 1, 99}, {8, 306, 8000, 512, 1, 99},
+            {24, 306, 0, 0, 0, 99, 0}, {24, 306, 0, 0, 0, 99, 1}, {24, 306, 0, 0, 0, 99, 2},
+            {24, 306, 8000, 0, 0, 99, 0}, {24, 306, 8000, 0, 0, 99, 1}, {24, 306, 8000, 0, 0, 99, 2},
+            {16, 306, 8000, 0, 1, 99, 0}, {16, 306, 8000, 0, 1, 99, 1},
         };
         int case_limit = argc > 3 ? atoi(argv[3]) : 1000;
         for (auto& c : cases) {
             if (case_limit-- <= 0) break;
             StreamArgs a{};
             a.base = wbuf; a.region = region; a.n_slots = c.n_slots; a.slot_bytes = slot;
-            a.phase_bytes = (c.phase_kb * 1024u / slot) * slot; a.n_phases = argc > 2 ? atoi(argv[2]) : 300; a.stall_ns = c.stall_ns; a.ahead = c.ahead_kb * 1024u; a.pf_chunk = slot; a.touch = c.touch; a.window = c.window;
+            a.phase_bytes = (c.phase_kb * 1024u / slot) * slot; a.n_phases = argc > 2 ? atoi(argv[2]) : 300; a.stall_ns = c.stall_ns; a.ahead = c.ahead_kb * 1024u; a.pf_chunk = slot; a.touch = c.touch; a.window = c.window; a.fence = c.fence;
             a.region = (region / slot) * slot;
             const size_t smem = 1024 + (size_t)c.n_slots * slot;
             void* args[] = {&a, &ctr, &out_ns, &sink};
@@ -386,8 +387,8 @@ int main(int argc, char** argv) {
             const double t = h.back() * 1e-9;
             const double bytes = (double)G * a.n_phases * a.phase_bytes;
             const double stall_total = a.n_phases * (double)c.stall_ns * 1e-9;
-            printf("D slots %2d win %2d phase %3u KB stall %5u ns ahead %4u KB touch %d: %.3f ms, %.0f GB/s overall, per phase %.2f us (stall %.1f + stream %.2f us = %.0f GB/s while streaming)\n",
-                   c.n_slots, c.window, a.phase_bytes / 1024, c.stall_ns, c.ahead_kb, c.touch, t * 1e3, bytes / t / 1e9, t / a.n_phases * 1e6, c.stall_ns * 1e-3,
+            printf("D fence %d slots %2d win %2d phase %3u KB stall %5u ns ahead %4u KB touch %d: %.3f ms, %.0f GB/s overall, per phase %.2f us (stall %.1f + stream %.2f us = %.0f GB/s while streaming)\n",
+                   c.fence, c.n_slots, c.window, a.phase_bytes / 1024, c.stall_ns, c.ahead_kb, c.touch, t * 1e3, bytes / t / 1e9, t / a.n_phases * 1e6, c.stall_ns * 1e-3,
                    (t - stall_total) / a.n_phases * 1e6, bytes / (t - stall_total) / 1e9);
         }
     }

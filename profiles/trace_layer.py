@@ -39,3 +39,11 @@ print(f"  QKV->attn   {st(t[:n_attn, 8] - t[:, 4].max())}")
 print(f"  attn->Wo    {st(t[:, 1] - t[:n_attn, 9].max())}")
 print(f"  Wo->W13     {st(t[:, 2] - t[:, 5].max())}")
 print(f"  W13->W2     {st(t[:, 3] - t[:, 6].max())}")
+
+for pk in range(4):
+    d = t[:, 4 + pk]
+    order = np.argsort(-np.nan_to_num(d))[:8]
+    print(f"phase {names[pk]:4s} slowest CTAs (drain finished): " + " ".join(f"{i}:{d[i]:.1f}" for i in order) + f"   | median {np.nanmedian(d):.1f}")
+    ic = t[:, pk]
+    order = np.argsort(-np.nan_to_num(ic))[:6]
+    print(f"           latest input complete: " + " ".join(f"{i}:{ic[i]:.1f}" for i in order) + f"   | median {np.nanmedian(ic):.1f}")
