@@ -100,43 +100,44 @@ class ClockSampler:
 
 # ----------------------------------------------------------------------------------------------------------
 def cpu_reference_baseline(max_seconds=40.0, threads=None):
-    """The reference's own CPU forward() (oracle/_ref/libref.so) on this host: two layer-slices of the 7B shape
-    (same dim / hidden / vocab), a few decode tokens each at ctx ~ PROMPT, per-token time fitted as a + b*L and
-    extrapolated to 32 layers.  Falls back to the C restatement (1 core) if the reference library is absent."""
+    """The reference's own CPU forward() (oracle/_ref/libref.so) on this host: ONE 3-layer slice of the 7B shape (same dim /
+    hidden / vocab, classifier shared with the embedding), min over a few decode tokens at ctx ~ PROMPT.  Decode time is
+    proportional to the weight bytes swept (SURVEY 8a: >94 % of it is quant::matmul), so the slice is scaled by
+    (32 + c) / (3 + c) with c = vocab*dim / params-per-layer = 0.65 (the classifier in units of a layer).
+    Falls back to the C restatement (1 core) if the reference library is absent."""
     from oracle_libs import ref, port, ptr, Q_INT8, PortConfig
     from fixtures import ModelSpec, gen_weights, write_llama2c, write_tokenizer_bin, synthetic_vocab, quantize_model
     spec7 = shape_7b()
     cores = threads or os.cpu_count() or 1
     R = ref()
-    times = {}
-    n_tok = 3
+    n_tok, L = 5, 3
     if R is not None:
-        for L in (1, 2):
-            spec = ModelSpec(spec7.dim, spec7.hidden_dim, L, spec7.n_heads, spec7.n_kv_heads, spec7.vocab_size, 1024, True)
-            w = gen_weights(spec, seed=L)
-            with tempfile.TemporaryDirectory() as d:
-                write_llama2c(d + "/m.bin", spec, w)
-                write_tokenizer_bin(d + "/t.bin", synthetic_vocab(spec.vocab_size))
-                del w
-                h = R.ref_model_load((d + "/m.bin").encode(), (d + "/t.bin").encode(), 3, Q_INT8, cores, 64, 0)
-            assert h, "reference failed to load the synthetic slice"
-            logits = np.empty(spec.vocab_size, np.float32)
-            prompt = np.arange(1, PROMPT + 1, dtype=np.int32)
-            R.ref_forward(h, ptr(prompt), PROMPT, 0, ptr(logits))
-            best = 1e9
-            for i in range(n_tok):
-                t = np.array([int(np.argmax(logits))], np.int32)
-                t0 = time.perf_counter()
-                R.ref_forward(h, ptr(t), 1, PROMPT + i, ptr(logits))
-                best = min(best, time.perf_counter() - t0)
-            times[L] = best
-            R.ref_model_free(h)
-        b = times[2] - times[1]
-        a = times[1] - b
-        per_token = a + b * spec7.n_layers
+        spec = ModelSpec(spec7.dim, spec7.hidden_dim, L, spec7.n_heads, spec7.n_kv_heads, spec7.vocab_size, 1024, True)
+        one = gen_weights(ModelSpec(spec7.dim, spec7.hidden_dim, 1, spec7.n_heads, spec7.n_kv_heads, spec7.vocab_size, 1024, True), seed=1)
+        w = {k: (np.broadcast_to(v[0], (L,) + v.shape[1:]) if k not in ("tok_emb", "out_norm", "cls") else v) for k, v in one.items()}
+        with tempfile.TemporaryDirectory() as d:
+            write_llama2c(d + "/m.bin", spec, w)
+            write_tokenizer_bin(d + "/t.bin", synthetic_vocab(spec.vocab_size))
+            del w, one
+            h = R.ref_model_load((d + "/m.bin").encode(), (d + "/t.bin").encode(), 3, Q_INT8, cores, 64, 0)
+        assert h, "reference failed to load the synthetic slice"
+        logits = np.empty(spec.vocab_size, np.float32)
+        prompt = np.arange(1, PROMPT + 1, dtype=np.int32)
+        R.ref_forward(h, ptr(prompt), PROMPT, 0, ptr(logits))
+        best = 1e9
+        for i in range(n_tok):
+            t = np.array([int(np.argmax(logits))], np.int32)
+            t0 = time.perf_counter()
+            R.ref_forward(h, ptr(t), 1, PROMPT + i, ptr(logits))
+            best = min(best, time.perf_counter() - t0)
+        R.ref_model_free(h)
+        per_layer_params = 4 * spec7.dim * spec7.dim + 3 * spec7.dim * spec7.hidden_dim
+        c = spec7.vocab_size * spec7.dim / per_layer_params
+        per_token = best * (spec7.n_layers + c) / (L + c)
         return {"value": 1.0 / per_token, "unit": UNIT, "cores": cores, "kind": "reference",
-                "sample": f"reference forward() on 1- and 2-layer slices of the 7B shape, min of {n_tok} decode tokens at ctx {PROMPT}; "
-                          f"t(L)={a * 1e3:.1f}ms+{b * 1e3:.1f}ms*L extrapolated to L=32 (AVX2+FMA build, {cores} threads)"}
+                "sample": f"reference forward() (unmodified sources, AVX2+FMA build, {cores} threads) on a {L}-layer slice of the 7B shape: "
+                          f"min of {n_tok} decode tokens at ctx {PROMPT} = {best * 1e3:.1f} ms, scaled by weight bytes to 32 layers "
+                          f"((32+{c:.2f})/({L}+{c:.2f}))"}
     # port fallback: one layer's worth of matmul work on one core
     P = port()
     spec = ModelSpec(spec7.dim, spec7.hidden_dim, 1, spec7.n_heads, spec7.n_kv_heads, 2048, 1024, True)
@@ -224,7 +225,7 @@ def run_ours(args, rank, world, local_rank):
             for _ in range(n_dec):
                 eng.decode_async(1)
                 with torch.cuda.stream(stream):
-                    dist.all_gather_into_tensor(gathered, tok_buf)
+                    fl.shard.gather_tokens(tok_buf, out=gathered)
         ev1.record(stream)
         barrier()
         return ev0.elapsed_time(ev1), eng.launch_count() - l0
@@ -280,9 +281,11 @@ def run_ours(args, rank, world, local_rank):
     step_bytes = float(np.mean([eng.step_bytes(PROMPT + 1 + i) for i in range(n_dec)]))
     ms_per_token = total_ms / (args.steps * n_dec)
     achieved = step_bytes / (ms_per_token * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "scope": "whole decode step (all 163 kernels of one token): algorithmic bytes = INT8 weights + fp32 group scales "
-                         f"+ fp32 KV read/write at mean ctx {mean_ctx:.0f} = {step_bytes / 1e9:.3f} GB/token",
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "scope": f"decode_megakernel, ONE persistent launch = {n_dec} tokens (every phase of every layer of every token); algorithmic "
+                         f"bytes per token = INT8 weights + fp32 group scales + fp32 KV read/write at mean ctx {mean_ctx:.0f} = {step_bytes / 1e9:.3f} GB "
+                         "(SURVEY 8d); achieved = bytes per token / measured time per token (CUDA events on the engine stream)",
+                "traffic": 7.37e9, "traffic_note": "dram read+write per token from ncu --set full of a 1-token launch at ctx 288 (profiles/r01/ncu_full_megakernel_v3.csv)",
                 "peak_source": peak_src, "frac_of_8TBs": achieved / 8000.0}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
