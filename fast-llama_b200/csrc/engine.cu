@@ -370,6 +370,7 @@ int setup_mega(fl_engine* e) {
     CK(e, cudaMemsetAsync(e->evlog, 0, sizeof(unsigned long long) * 2 * 4096, e->stream));
     MegaParams& p = e->mega;
     p.layers = e->mega_layers; p.cls = e->rk_cls.d; p.out_norm = e->out_norm; p.emb = e->emb;
+    p.att_norm = e->att_norm; p.ffn_norm = e->ffn_norm;
     p.off_qkv = e->rk_off[RK_QKV]; p.off_wo = e->rk_off[RK_WO]; p.off_w13 = e->rk_off[RK_W13]; p.off_w2 = e->rk_off[RK_W2]; p.off_cls = e->rk_off[RK_CLS];
     p.x1t = e->x1t; p.qkvt = e->qkvt; p.attnt = e->attnt; p.hdt = e->hdt; p.score_t = e->score_t; p.am = e->am; p.logits = e->logits;
     p.rope = e->rope; p.out_cap = e->out_cap; p.score_stride = score_stride;
@@ -393,6 +394,7 @@ int setup_mega(fl_engine* e) {
     p.off_xs = (int)off; off += al((size_t)nkc_max * gps * 4, 128);
     p.off_vbars = (int)off; off += 128;
     p.off_pairs = (int)off; off += 2 * kPairGroups * 32 * 8;             // two pair buffers (consumers -> chain warp)
+    p.off_psrc = (int)off; off += al((size_t)(4 * L + 1) * 8, 128);      // this CTA's weight-stream start of every phase
     // [activation image | transposed fp32 vector]: contiguous, because attention (which uses neither) turns the whole
     // range into its ring of V chunks
     const size_t xq_bytes = al((size_t)nkc_max * kStageRowBytes, 128), xt_bytes = al((size_t)c.dim * 4, 128);
