@@ -171,6 +171,8 @@ int alloc_rk(fl_engine* e, RkMat& m, int kind) {
 }
 
 bool mega_supported(const fl_config& c, int n_sms) {
+    const int max_rows = (c.vocab_size > c.hidden_dim ? c.vocab_size : c.hidden_dim) / n_sms + 1;     // rows of a CTA: at most kGeomMaxTiles tiles
+    if (max_rows > kGeomMaxTiles * kTileRows || c.dim + 2 * c.head_size * c.n_kv_heads > n_sms * kGeomMaxTiles * kTileRows) return false;
     return !(c.flags & FL_FLAG_NO_MEGAKERNEL) && c.n_heads <= n_sms && c.dim <= 6144;
 }
 
@@ -395,6 +397,7 @@ int setup_mega(fl_engine* e) {
     p.off_vbars = (int)off; off += 128;
     p.off_pairs = (int)off; off += 2 * kPairGroups * 32 * 8;             // two pair buffers (consumers -> chain warp)
     p.off_psrc = (int)off; off += al((size_t)(4 * L + 1) * 8, 128);      // this CTA's weight-stream start of every phase
+    p.off_geom = (int)off; off += 5 * kGeomStride * 4;                   // this CTA's tile / superblock geometry of the five phase kinds
     // [activation image | transposed fp32 vector]: contiguous, because attention (which uses neither) turns the whole
     // range into its ring of V chunks
     const size_t xq_bytes = al((size_t)nkc_max * kStageRowBytes, 128), xt_bytes = al((size_t)c.dim * 4, 128);

@@ -96,7 +96,7 @@ struct MegaParams {
     int window;                       // max stages in flight (issued, not yet landed); >= n_slots: no limit
     uint32_t epoch;                   // tags of this launch are epoch + 1 ... epoch + n_steps * (n_layers + 1) * 8
     // dynamic shared memory carve-up (byte offsets)
-    int off_ring, off_xq, off_xs, off_xt, off_chain, off_att, off_misc, off_bars, off_vstage, off_vbars, off_pairs, off_psrc;
+    int off_ring, off_xq, off_xs, off_xt, off_chain, off_att, off_misc, off_bars, off_vstage, off_vbars, off_pairs, off_psrc, off_geom;
     int v_chunk_rows, n_vchunks;     // V ring of the attention part: n_vchunks chunks of v_chunk_rows rows x HS/cph floats
 };
 
@@ -284,6 +284,24 @@ __device__ __forceinline__ const uint8_t* phase_stream(const MegaParams& p, int 
     if (ph == 1) return L->wo + p.off_wo[blockIdx.x];
     if (ph == 2) return L->w13 + p.off_w13[blockIdx.x];
     return L->w2 + p.off_w2[blockIdx.x];
+}
+
+// Geometry of the five phase kinds (QKV, Wo, W1/W3, W2, classifier) for THIS CTA, computed once at kernel start into shared
+// memory: the divisions behind rk_part / rk_tile / the superblock split cost ~1 us per phase when redone by every warp.
+constexpr int kGeomStride = 32;     // ints per kind: M, K, tt, rb, nr, nt, nkc, sk, nsb, then nt + 1 tile boundaries (local rows)
+constexpr int kGeomMaxTiles = 20;
+enum { PG_M = 0, PG_K, PG_TT, PG_RB, PG_NR, PG_NT, PG_NKC, PG_SK, PG_NSB, PG_LR };
+template <int QT, int GS>
+__device__ __forceinline__ void fill_geometry(const MegaParams& p, int* geom, int kind) {
+    using RK = Rk<QT, GS>;
+    const PhaseShape s = phase_shape(p, kind == 4 ? 4 * p.n_layers : kind);
+    const RkPart pt = rk_part(s.M, blockIdx.x, gridDim.x);
+    int* g = geom + kind * kGeomStride;
+    g[PG_M] = s.M; g[PG_K] = s.K; g[PG_TT] = s.tt; g[PG_RB] = pt.rb; g[PG_NR] = pt.nr; g[PG_NT] = pt.nt;
+    g[PG_NKC] = ceil_div(s.K * RK::ES, kStageRowBytes);
+    g[PG_SK] = kPairGroups / s.tt / RK::GPS;
+    g[PG_NSB] = ceil_div(g[PG_NKC], g[PG_SK]);
+    for (int t = 0; t <= pt.nt && t <= kGeomMaxTiles; ++t) g[PG_LR + t] = pt.nt ? pt.nr * t / pt.nt : 0;
 }
 
 // ---------------------------------------------------------------------------------------------- activation rebuild
@@ -844,7 +862,9 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
     {
         const uint8_t** psrc = reinterpret_cast<const uint8_t**>(smem + p.off_psrc);
         for (int pi = tid; pi < n_phases; pi += kMegaThreads) psrc[pi] = phase_stream(p, pi);
+        if (tid >= 64 && tid < 69) fill_geometry<QT, GS>(p, reinterpret_cast<int*>(smem + p.off_geom), tid - 64);
     }
+    const int* geom = reinterpret_cast<const int*>(smem + p.off_geom);
     __syncthreads();
 
     if (warp == kConsumerWarps) {
@@ -861,15 +881,12 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
             for (int step = 0; step < p.n_steps; ++step) {
 #pragma unroll 1
                 for (int pi = 0; pi < n_phases; ++pi) {
-                    const PhaseShape ph = phase_shape(p, pi);
-                    const RkPart pt = rk_part(ph.M, blockIdx.x, gridDim.x);
-                    const int n_stages = ceil_div(ph.K * RK::ES, kStageRowBytes) * ph.tt;      // per tile
+                    const int* pg = geom + ((pi == n_phases - 1) ? 4 : (pi & 3)) * kGeomStride;
+                    const int n_stages = pg[PG_NKC] * pg[PG_TT];      // per tile
                     const uint8_t* src = reinterpret_cast<const uint8_t* const*>(smem + p.off_psrc)[pi];      // the stream is laid out in issue order
 #pragma unroll 1
-                    for (int t = 0; t < pt.nt; ++t) {
-                        int lr0, R;
-                        rk_tile(pt, t, lr0, R);
-                        const uint32_t bytes = (uint32_t)RK::stage_bytes(R);
+                    for (int t = 0; t < pg[PG_NT]; ++t) {
+                        const uint32_t bytes = (uint32_t)RK::stage_bytes(pg[PG_LR + t + 1] - pg[PG_LR + t]);
 #pragma unroll 1
                         for (int st = 0; st < n_stages; ++st) {
                             if (window < (uint32_t)n_slots && sc >= window) {
@@ -906,22 +923,21 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
             const uint32_t tbase = p.epoch + 1u + (uint32_t)step * (uint32_t)(p.n_layers + 1) * kTagsPerLayer;
 #pragma unroll 1
             for (int pi = 0; pi < n_phases; ++pi) {
-                const PhaseShape ph = phase_shape(p, pi);
                 const int layer = pi >> 2, pk = (pi == n_phases - 1) ? 4 : (pi & 3);
+                const int* pg = geom + pk * kGeomStride;
+                struct { int tt, M; } ph = {pg[PG_TT], pg[PG_M]};
                 pf.ev = ((step == p.n_steps - 1) && (layer == p.n_layers / 2) && pk < 4 && p.evlog && (p.debug_skip & 16) && (blockIdx.x == 7 || blockIdx.x == gridDim.x - 3)) ? p.evlog + (blockIdx.x == 7 ? 0 : 4096) : nullptr;
                 const uint32_t tl = tbase + (uint32_t)layer * kTagsPerLayer;
                 uint2* out = (pk == 0) ? p.qkvt : (pk == 2) ? p.hdt : p.x1t;
                 const uint32_t tag_out = tl + ((pk == 0) ? 1u : (pk == 1) ? 4u : (pk == 2) ? 5u : 6u);
-                const RkPart pt = rk_part(ph.M, blockIdx.x, gridDim.x);
-                const int nkc = ceil_div(ph.K * RK::ES, kStageRowBytes);
-                const int sk = kPairGroups / ph.tt / RK::GPS, nsb = ceil_div(nkc, sk);
+                struct { int rb, nt; } pt = {pg[PG_RB], pg[PG_NT]};
+                const int nkc = pg[PG_NKC], sk = pg[PG_SK], nsb = pg[PG_NSB];
                 const int gstride = (kPairGroups / ph.tt) * 32;          // float2s per sub-stream in a pair buffer
                 float best_v = -INFINITY;
                 int best_i = 0x7fffffff;
 #pragma unroll 1
                 for (int t = 0; t < pt.nt; ++t) {
-                    int lr0, R;
-                    rk_tile(pt, t, lr0, R);
+                    const int lr0 = pg[PG_LR + t], R = pg[PG_LR + t + 1] - lr0;
                     const int row = pt.rb + lr0 + lane;
                     const bool live = lane < R;
                     // residual input of this row (x1 += tmp, tensor.cpp:723): its word was validated by the consumers' earlier build
@@ -998,6 +1014,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
     const bool attn_cta = (int)blockIdx.x < n_attn_ctas;
     const int my_head = blockIdx.x / p.cph, my_part = blockIdx.x % p.cph;
     uint32_t sc = 0, cseq = 0, sbseq = 0;      // stages / K chunks / superblocks so far
+    uint32_t sb_sl = 0, sb_pr = 0;             // ring slot and parity of stage `sc`, advanced incrementally
     Prof pf;
     pf.p = p.prof ? p.prof + (size_t)blockIdx.x * 32 : nullptr;
     pf.t0 = pf.p ? (unsigned long long)clock64() : 0ull;
@@ -1043,22 +1060,20 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
             }
             pf.stop(tid, 1);
             pf.log(lane, warp, 7, pk);          // drain starts
-            const PhaseShape ph = phase_shape(p, pi);        // evaluated after the build: nothing of it lives across the build
+            const int* pg = geom + pk * kGeomStride;
+            struct { int tt, M; } ph = {pg[PG_TT], pg[PG_M]};
             // ---- drain this CTA's stages of the phase
             uint2* out = (pk == 0) ? p.qkvt : (pk == 2) ? p.hdt : p.x1t;
             const uint32_t tag_out = tl + ((pk == 0) ? 1u : (pk == 1) ? 4u : (pk == 2) ? 5u : 6u);
             {
-                const RkPart pt = rk_part(ph.M, blockIdx.x, gridDim.x);
-                const int nkc = ceil_div(ph.K * RK::ES, kStageRowBytes);
-                const int sk = kPairGroups / ph.tt / RK::GPS, nsb = ceil_div(nkc, sk);
+                struct { int nt; } pt = {pg[PG_NT]};
+                const int nkc = pg[PG_NKC], sk = pg[PG_SK], nsb = pg[PG_NSB];
                 const int gstride = (kPairGroups / ph.tt) * 32;          // float2s per sub-stream in a pair buffer
-                uint32_t sb_sl = sc % (uint32_t)n_slots, sb_pr = (sc / (uint32_t)n_slots) & 1u;       // ring position of stage `sc`, advanced incrementally
                 if (pf.p && tid == kProfThread) atomicAdd(pf.p + 20, (unsigned long long)(ld_shared_volatile_u32(issued) - sc));   // stages the producer is ahead at drain start
                 const uint32_t drain_sc0 = sc;
 #pragma unroll 1
                 for (int t = 0; t < pt.nt; ++t) {
-                    int lr0, R;
-                    rk_tile(pt, t, lr0, R);
+                    const int R = pg[PG_LR + t + 1] - pg[PG_LR + t];
                     const bool live = lane < R;
 #pragma unroll 1
                     for (int j = 0; j < nsb; ++j) {
