@@ -37,15 +37,16 @@ def shape_7b():
 
 
 # ----------------------------------------------------------------------------------------------------------
-def synth_int8_model(spec, seed=0):
-    """Random INT8 payloads + fp32 group scales with realistic magnitudes (no 27 GB float model is materialised)."""
+def synth_int8_model(spec, seed=0, int16=False, gs=64):
+    """Random INT8 (or INT16) payloads + fp32 group scales with realistic magnitudes (no 27 GB float model is materialised)."""
     from oracle_libs import (T_TOK_EMB, T_ATT_NORM, T_WQ, T_WK, T_WV, T_WO, T_FFN_NORM, T_W1, T_W2, T_W3, T_OUT_NORM, T_CLS)
     rng = np.random.default_rng(seed)
     d, h, kv = spec.dim, spec.hidden_dim, spec.kv_dim
 
     def qmat(rows, cols, sd):
-        q = np.clip(np.rint(rng.standard_normal((rows, cols), dtype=np.float32) * 40.0), -127, 127).astype(np.int8)
-        s = (np.float32(sd / 40.0) * (0.75 + 0.5 * rng.random((rows, cols // 64), dtype=np.float32))).astype(np.float32)
+        amp, lim, dt = (1800.0, 5792, np.int16) if int16 else (40.0, 127, np.int8)
+        q = np.clip(np.rint(rng.standard_normal((rows, cols), dtype=np.float32) * np.float32(amp)), -lim, lim).astype(dt)
+        s = (np.float32(sd / amp) * (0.75 + 0.5 * rng.random((rows, cols // gs), dtype=np.float32))).astype(np.float32)
         return q, s
 
     base = {T_WQ: qmat(d, d, d ** -0.5), T_WK: qmat(kv, d, d ** -0.5), T_WV: qmat(kv, d, d ** -0.5), T_WO: qmat(d, d, d ** -0.5),
@@ -282,7 +283,7 @@ def run_ours(args, rank, world, local_rank):
     ms_per_token = total_ms / (args.steps * n_dec)
     achieved = step_bytes / (ms_per_token * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "scope": f"decode_megakernel, ONE persistent launch = {n_dec} tokens (every phase of every layer of every token); algorithmic "
+                "scope": f"decode_megakernel, {'ONE persistent launch' if world == 1 else 'one launch per token (+ token all-gather),'} = {n_dec} tokens (every phase of every layer of every token); algorithmic "
                          f"bytes per token = INT8 weights + fp32 group scales + fp32 KV read/write at mean ctx {mean_ctx:.0f} = {step_bytes / 1e9:.3f} GB "
                          "(SURVEY 8d); achieved = bytes per token / measured time per token (CUDA events on the engine stream)",
                 "traffic": 7.37e9, "traffic_note": "dram read+write per token from ncu --set full of a 1-token launch at ctx 288 (profiles/r01/ncu_full_megakernel_v3.csv)",

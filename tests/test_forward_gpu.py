@@ -137,6 +137,54 @@ def test_kv_slots_are_independent_and_batch_matches_single(fl):
     eng.close()
 
 
+LONG_CASES = [
+    # name, spec, quant, group, new tokens: long enough that the persistent kernel refills its V-chunk ring (context beyond the
+    # chunks that fit shared memory), takes a second batch of K rows (> 96 keys per CTA of a head) and crosses chunk boundaries
+    ("tiny-int8-450", TINY, Q_INT8, 64, 450, 11),
+    ("tiny64-int8-330", TINY64, Q_INT8, 64, 330, 11),
+    ("gqa-int8-200", GQA, Q_INT8, 64, 200, 12),
+    ("tiny-int16-130", TINY, Q_INT16, 64, 130, 11),
+]      # seeds chosen so that the oracle's greedy run does not hit the end token (id 0) before n_new
+
+
+@pytest.mark.parametrize("name,spec,qt,gs,n_new,seed", LONG_CASES, ids=[c[0] for c in LONG_CASES])
+def test_long_context_tokens_and_logits_bit_exact(fl, name, spec, qt, gs, n_new, seed):
+    """Device-resident greedy generation (fl_generate_greedy: one persistent launch for all steps) against the oracle run
+    token by token; the logits of the last step and every token id must be identical."""
+    w = gen_weights(spec, seed=seed)
+    qm = quantize_model(spec, w, qt, gs)
+    pm = make_port_model(spec, qm, qt, gs)
+    P = port()
+    prompt = prompt_tokens(spec, 7, seed=9)
+    logits = np.empty(spec.vocab_size, np.float32)
+    P.port_forward(pm, ptr(prompt), prompt.size, 0, ptr(logits))
+    want = [P.port_argmax(ptr(logits), spec.vocab_size)]
+    pos = prompt.size
+    for _ in range(n_new):
+        if want[-1] == 0:
+            break
+        t = np.array([want[-1]], np.int32)
+        P.port_forward(pm, ptr(t), 1, pos, ptr(logits))
+        want.append(P.port_argmax(ptr(logits), spec.vocab_size))
+        pos += 1
+    eng = make_engine(fl, spec, qm, qt, gs)
+    got = eng.generate_greedy(prompt, n_new).tolist()
+    assert got == want, (name, next(i for i, (a, b) in enumerate(zip(got, want)) if a != b))
+    assert len(want) > min(n_new, 100), "generation ended too early for this test to mean anything"
+    # the logits of the last forward are still on the device: bit-identical to the oracle's
+    if want[-1] != 0:
+        got_logits = eng.tap("logits")[:spec.vocab_size]
+        assert np.array_equal(bits(got_logits), bits(logits)), name
+    # and stepping on through fl_forward (one launch per token) from the same cache continues identically
+    t = np.array([want[-1]], np.int32)
+    if want[-1] != 0:
+        P.port_forward(pm, ptr(t), 1, pos, ptr(logits))
+        nxt = eng.forward(t, pos)
+        assert np.array_equal(bits(nxt), bits(logits)), name
+    P.port_model_free(pm)
+    eng.close()
+
+
 def test_error_behaviour(fl):
     spec = TINY
     with pytest.raises(fl.FlError):
