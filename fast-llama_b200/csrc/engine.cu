@@ -395,16 +395,17 @@ int setup_mega(fl_engine* e) {
     p.off_att = (int)off; off += al((size_t)c.max_seq_len * 4 + 64, 128);
     p.off_xs = (int)off; off += al((size_t)nkc_max * gps * 4, 128);
     p.off_vbars = (int)off; off += 128;
-    p.off_pairs = (int)off; off += 2 * kPairGroups * 32 * 8;             // two pair buffers (consumers -> chain warp)
     p.off_psrc = (int)off; off += al((size_t)(4 * L + 1) * 8, 128);      // this CTA's weight-stream start of every phase
     p.off_geom = (int)off; off += 5 * kGeomStride * 4;                   // this CTA's tile / superblock geometry of the five phase kinds
-    // [activation image | transposed fp32 vector]: contiguous, because attention (which uses neither) turns the whole
-    // range into its ring of V chunks
+    // [activation image | pair buffers]: contiguous, because attention (which uses neither) turns the whole range into its ring
+    // of V chunks.  The transposed fp32 vector of the rmsnorm rebuild lives on top of the pair buffers: it is written only
+    // after the rebuild's input is complete, i.e. after this CTA's own chain warp has published (and stopped reading pairs).
     const size_t xq_bytes = al((size_t)nkc_max * kStageRowBytes, 128), xt_bytes = al((size_t)c.dim * 4, 128);
+    const size_t pair_bytes = 2 * (size_t)kPairGroups * 32 * 8;
     p.off_vstage = (int)off;
     p.off_chain = (int)off;
     p.off_xq = (int)off; off += xq_bytes;
-    p.off_xt = (int)off; off += xt_bytes;
+    p.off_pairs = (int)off; p.off_xt = (int)off; off += (pair_bytes > xt_bytes ? pair_bytes : xt_bytes);
     size_t vbytes = off - p.off_vstage;
     if (vbytes < 2 * 4096) { off += 2 * 4096 - vbytes; vbytes = 2 * 4096; }
     p.n_vchunks = (int)(vbytes / 4096) > 16 ? 16 : (int)(vbytes / 4096);

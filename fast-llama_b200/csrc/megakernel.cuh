@@ -52,7 +52,7 @@ namespace fl {
 constexpr int kConsumerWarps = 8;
 constexpr int kConsumerThreads = kConsumerWarps * 32;
 constexpr int kMegaThreads = kConsumerThreads + 64;     // + TMA producer warp + chain warp
-constexpr int kPairGroups = 32;                          // groups (all sub-streams together) per superblock = per pair buffer (8 KB; 64 measured slower: 2 fewer ring stages)
+constexpr int kPairGroups = 64;                          // groups (all sub-streams together) per superblock = per pair buffer (16 KB)
 constexpr int kTagsPerLayer = 8;
 constexpr int kSerialWarp = kConsumerWarps - 1;   // runs the single-warp serial sections: the scheduler favours the highest warp id of a
                                                   // sub-partition, and warp 7 shares its sub-partition only with warp 3 (not with the producer / chain warps)
@@ -175,7 +175,9 @@ struct Prof {
     unsigned long long* ev;           // event log of this CTA while the traced layer runs, else NULL
     unsigned int* evn;                // its event counter (shared memory: a global atomic with a return value costs a round trip)
     __device__ __forceinline__ void log(int lane, int warp, int type, int arg) {
+#ifdef FL_EVLOG          // the per-warp event log is a debugging build: it costs ~10 KB of code the instruction cache needs
         if (ev && lane == 0) { const unsigned int i = atomicAdd(evn, 1u); if (i < 4095u) ev[1 + i] = (gtimer() << 24) | ((unsigned long long)warp << 20) | ((unsigned long long)type << 12) | (unsigned long long)(arg & 0xfff); ev[0] = i + 1; }
+#endif
     }
     // absolute timestamp of one event of the traced layer (slots 22..31): skew and latency of one exchange, see profiles/trace_layer.py
     __device__ __forceinline__ void mark(int tid, int slot, bool on) {
@@ -550,8 +552,7 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 // cache keeps 4 consecutive positions of a head dim adjacent ([t/4][DW][4]): one LDS.128 brings 4 rows, the loads of the
 // next 16 rows are issued before the current 16 dependent FMAs, and blocks of 16 rows whose weights all pass the threshold
 // (slow == 0: virtually always) take an FFMA-only path.  vb points at this thread's dim inside the chunk: row r is vb[(r/4)*DW*4 + r%4].
-template <int DW>
-__device__ __forceinline__ float pv_rows(const float* vb, const float* wp, int i, int rows, uint32_t slow, float o) {
+__device__ __forceinline__ float pv_rows(const float* vb, const float* wp, int DW, int i, int rows, uint32_t slow, float o) {
     auto one = [&](int r) { const float w = wp[r]; if (fabsf(w) > 1e-15f) o = __fmaf_rn(vb[(r >> 2) * (DW * 4) + (r & 3)], w, o); };
     for (; i < rows && (i & 15); ++i) one(i);
     if (i + 16 <= rows) {
@@ -595,7 +596,7 @@ __device__ __forceinline__ float pv_rows(const float* vb, const float* wp, int i
 
 template <int HS>
 __device__ __forceinline__ void attention_part(const MegaParams& p, uint8_t* smem, int layer, int qh, int part, int pos, int bs,
-                                               uint32_t tag_qkv, uint32_t tag_score, uint32_t tag_out, int tid, Prof& pf) {
+                                               uint32_t tag_qkv, uint32_t tag_score, uint32_t tag_out, uint32_t phases_drained, int tid, Prof& pf) {
     constexpr int EPL = HS / 8;
     const int cph = p.cph;
     const int DW = HS / cph;                                // head dims owned by this part
@@ -633,7 +634,10 @@ __device__ __forceinline__ void attention_part(const MegaParams& p, uint8_t* sme
     if (tid < 32) slowbits[tid] = 0u;
     const int pvt = tid - (kConsumerThreads - DW);          // index inside the PV group (the last DW consumer threads), < 0 for the others
     if (pvt == 0) {
-        fence_proxy_async();                                // the ring aliases memory the generic proxy wrote (activation image)
+        // the ring also covers the pair buffers: wait until this CTA's chain warp has finished the QKV phase (it trails the
+        // consumers by one superblock at most)
+        while ((int)(ld_shared_volatile_u32(reinterpret_cast<uint32_t*>(smem + p.off_misc) + 29) - phases_drained) < 0) __nanosleep(50);
+        fence_proxy_async();                                // the ring aliases memory the generic proxy wrote (activation image, pairs)
         for (int c = 0; c < min(NCH, n_chunks); ++c) issue_v(c);
     }
 
@@ -806,12 +810,7 @@ __device__ __forceinline__ void attention_part(const MegaParams& p, uint8_t* sme
             const uint32_t slow = (slowbits[(c * VR) >> 9] >> (((c * VR) >> 4) & 31));        // VR <= 64 rows: at most 4 blocks, inside one word
             int i = 0;
             if (c == 0) { o = __fmul_rn(vb[0], wp[0]); i = 1; }          // row 0 of my dim
-            switch (DW) {
-                case 32: o = pv_rows<32>(vb, wp, i, rows, slow, o); break;
-                case 64: o = pv_rows<64>(vb, wp, i, rows, slow, o); break;
-                case 128: o = pv_rows<128>(vb, wp, i, rows, slow, o); break;
-                default: o = pv_rows<16>(vb, wp, i, rows, slow, o); break;
-            }
+            o = pv_rows(vb, wp, DW, i, rows, slow, o);
             wp += VR;
             { const long long t = clock64(); c_loop += t - ck; ck = t; }
             // the chunk is consumed: refill its slot with chunk c + NCH
@@ -856,6 +855,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
         reinterpret_cast<uint32_t*>(smem + p.off_misc)[24] = 0u;      // pair buffer 0 / 1: times released by the chain warp
         reinterpret_cast<uint32_t*>(smem + p.off_misc)[25] = 0u;
         reinterpret_cast<uint32_t*>(smem + p.off_misc)[31] = 0u;
+        reinterpret_cast<uint32_t*>(smem + p.off_misc)[29] = 0u;      // phases the chain warp has finished
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     const int n_phases = 4 * p.n_layers + 1;
@@ -915,6 +915,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
         // ================= chain warp =================
         // Follows the consumers' schedule superblock by superblock; lane i owns row i of the current tile.
         uint32_t sbseq = 0;                                  // superblocks so far (buffer = sbseq & 1)
+        uint32_t phases_done = 0;
         Prof pf;
         pf.p = p.prof ? p.prof + (size_t)blockIdx.x * 32 : nullptr; pf.t0 = 0ull; pf.trace_slot = -1; pf.ev = nullptr;
         pf.evn = reinterpret_cast<unsigned int*>(smem + p.off_misc) + 31;
@@ -987,6 +988,8 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
                     }
                     pf.log(lane, 9, 6, t);
                 }
+                __syncwarp();
+                if (lane == 0) st_shared_volatile_u32(reinterpret_cast<uint32_t*>(smem + p.off_misc) + 29, ++phases_done);      // pair buffers are idle until the next drain
                 if (pk == 4) {
                     // per-CTA argmax partial (sampler.cpp:36-46: first index of the strict maximum)
                     const uint32_t tag_am = tbase + (uint32_t)p.n_layers * kTagsPerLayer + 1u;
@@ -1015,6 +1018,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
     const int my_head = blockIdx.x / p.cph, my_part = blockIdx.x % p.cph;
     uint32_t sc = 0, cseq = 0, sbseq = 0;      // stages / K chunks / superblocks so far
     uint32_t sb_sl = 0, sb_pr = 0;             // ring slot and parity of stage `sc`, advanced incrementally
+    uint32_t phases_drained = 0;
     Prof pf;
     pf.p = p.prof ? p.prof + (size_t)blockIdx.x * 32 : nullptr;
     pf.t0 = pf.p ? (unsigned long long)clock64() : 0ull;
@@ -1121,6 +1125,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
                     }
                 }
             }
+            ++phases_drained;
             pf.stop(tid, 2 + pk);
             if (pf.p && traced && lane == 0) atomicMax(pf.p + 26 + pk, gtimer());
             if (pk == 4) {
@@ -1160,7 +1165,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
             if (pk == 0 && attn_cta) {
                 // ---- attention (transformer.cpp:136, :397-455)
                 consumer_sync();            // the V stage aliases the activation image the other warps may still be draining with
-                attention_part<HS>(p, smem, layer, my_head, my_part, pos, bs, tl + 1u, tl + 2u, tl + 3u, tid, pf);
+                attention_part<HS>(p, smem, layer, my_head, my_part, pos, bs, tl + 1u, tl + 2u, tl + 3u, phases_drained, tid, pf);
             }
         }
         pf.stop(tid, 18);

@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(320, 1) k(int variant, int which_warp, int n_r
         t0 = clock64();
         for (int rep = 0; rep < 8; ++rep) {
             const float* wp = att;
-            for (int c = 0; c < n_rows / 32; ++c) { o = pv_rows<32>(v + c * 1024 + lane * 4, wp, c == 0 ? 1 : 0, 32, 0u, o); wp += 32; }
+            for (int c = 0; c < n_rows / 32; ++c) { o = pv_rows(v + c * 1024 + lane * 4, wp, 32, c == 0 ? 1 : 0, 32, 0u, o); wp += 32; }
         }
         t1 = clock64();
         if (lane == 0) { cyc[blockIdx.x] = (t1 - t0) / 8; *stop = 1; }
