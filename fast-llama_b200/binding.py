@@ -28,7 +28,9 @@ class FlConfig(C.Structure):
 
 
 def lib_path():
-    return os.path.join(HERE, "libfastllama_b200.so")
+    # FL_PROF_LIB=1 selects the build with the in-kernel profiling counters compiled in (profiles/*.py set it)
+    name = "libfastllama_b200_prof.so" if os.environ.get("FL_PROF_LIB") == "1" else "libfastllama_b200.so"
+    return os.path.join(HERE, name)
 
 
 _lib = None

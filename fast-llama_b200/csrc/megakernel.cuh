@@ -170,7 +170,9 @@ __device__ __forceinline__ void st_relaxed_v4(uint4* p, uint4 v) {
 struct Prof {
     unsigned long long* p; unsigned long long t0; int trace_slot;   // trace_slot >= 0: the current build records when its input was complete
     __device__ __forceinline__ void stop(int tid, int cat) {
+#ifdef FL_PROFILE        // libfastllama_b200_prof.so only: ~30 call sites are 6 KB of code the instruction cache needs
         if (p && tid == kProfThread) { const unsigned long long t = (unsigned long long)clock64(); atomicAdd(p + cat, t - t0); t0 = t; }      // SM cycles: %globaltimer costs ~0.2 us a read
+#endif
     }
     unsigned long long* ev;           // event log of this CTA while the traced layer runs, else NULL
     unsigned int* evn;                // its event counter (shared memory: a global atomic with a return value costs a round trip)
@@ -181,7 +183,9 @@ struct Prof {
     }
     // absolute timestamp of one event of the traced layer (slots 22..31): skew and latency of one exchange, see profiles/trace_layer.py
     __device__ __forceinline__ void mark(int tid, int slot, bool on) {
+#ifdef FL_PROFILE
         if (p && on && tid == kProfThread) p[slot] = gtimer();
+#endif
     }
 };
 
@@ -827,7 +831,9 @@ __device__ __forceinline__ void attention_part(const MegaParams& p, uint8_t* sme
         (void)c_wait; (void)c_loop; (void)c_rest;
         if (pvt == 0) {
             *vcount = vbase + (uint32_t)n_chunks;
+#ifdef FL_PROFILE
             if (pf.p && pf.trace_slot >= 0) pf.p[31] = gtimer();
+#endif
         }
     }
     pf.stop(tid, 15);
@@ -1073,7 +1079,9 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
                 struct { int nt; } pt = {pg[PG_NT]};
                 const int nkc = pg[PG_NKC], sk = pg[PG_SK], nsb = pg[PG_NSB];
                 const int gstride = (kPairGroups / ph.tt) * 32;          // float2s per sub-stream in a pair buffer
+#ifdef FL_PROFILE
                 if (pf.p && tid == kProfThread) atomicAdd(pf.p + 20, (unsigned long long)(ld_shared_volatile_u32(issued) - sc));   // stages the producer is ahead at drain start
+#endif
                 const uint32_t drain_sc0 = sc;
 #pragma unroll 1
                 for (int t = 0; t < pt.nt; ++t) {
@@ -1127,7 +1135,9 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
             }
             ++phases_drained;
             pf.stop(tid, 2 + pk);
+#ifdef FL_PROFILE
             if (pf.p && traced && lane == 0) atomicMax(pf.p + 26 + pk, gtimer());
+#endif
             if (pk == 4) {
                 // ---- argmax (sampler.cpp:36-46): the chain warps published one partial per CTA as tagged words; every CTA
                 //      reduces all of them, so every CTA knows the next token without another round trip

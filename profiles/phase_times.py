@@ -1,5 +1,6 @@
 """Per-category time inside the persistent decode kernel (FL_FLAG_PROFILE), LLaMA2-7B-shaped INT8."""
 import os, sys
+os.environ.setdefault('FL_PROF_LIB', '1')     # the library build with the profiling counters compiled in
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))

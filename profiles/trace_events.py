@@ -1,6 +1,7 @@
 """Event log of the traced layer (middle layer, last decode step) on one attention CTA (7) and one other CTA (n-3):
 per warp: stage wait / ready / done, chain token receive / send, build and drain starts.  Prints a per-phase timeline."""
 import os, sys
+os.environ.setdefault('FL_PROF_LIB', '1')     # the library build with the profiling counters compiled in
 os.environ['FL_DEBUG_SKIP'] = '16'      # bit 4: enable the event log
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

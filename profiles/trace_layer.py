@@ -3,6 +3,7 @@ slots: 22+pk = input of phase pk complete (tags valid), 26+pk = drain of phase p
 31 = attention finished.  Prints, per phase, the skew of the producers and the latency from the LAST producer's finish to
 each consumer's "input complete"."""
 import os, sys
+os.environ.setdefault('FL_PROF_LIB', '1')     # the library build with the profiling counters compiled in
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
