@@ -384,7 +384,8 @@ int setup_mega(fl_engine* e) {
     const int cph = e->cph;
     p.cph = cph;
     const int dw = c.head_size / cph;
-    p.v_chunk_rows = 1024 / dw;                     // V chunks of 4 KB
+    const int v_chunk_bytes = getenv("FL_VCHUNK") ? atoi(getenv("FL_VCHUNK")) : 16384;     // tuning knob (profiles/r01: PV costs ~0.45 us per chunk on top of the chain; 4 KB 178, 8 KB 138, 16 KB 122 us per token)
+    p.v_chunk_rows = v_chunk_bytes / 4 / dw;          // V chunks of 16 KB: rows x dims-per-part fp32
     // shared memory carve-up
     const int kmax = c.dim > c.hidden_dim ? c.dim : c.hidden_dim;
     const int nkc_max = ceil_div(kmax * es, kStageRowBytes);
@@ -407,8 +408,8 @@ int setup_mega(fl_engine* e) {
     p.off_xq = (int)off; off += xq_bytes;
     p.off_pairs = (int)off; p.off_xt = (int)off; off += (pair_bytes > xt_bytes ? pair_bytes : xt_bytes);
     size_t vbytes = off - p.off_vstage;
-    if (vbytes < 2 * 4096) { off += 2 * 4096 - vbytes; vbytes = 2 * 4096; }
-    p.n_vchunks = (int)(vbytes / 4096) > 16 ? 16 : (int)(vbytes / 4096);
+    if (vbytes < 2 * (size_t)v_chunk_bytes) { off += 2 * v_chunk_bytes - vbytes; vbytes = 2 * v_chunk_bytes; }
+    p.n_vchunks = (int)(vbytes / v_chunk_bytes) > 16 ? 16 : (int)(vbytes / v_chunk_bytes);
     int max_smem = 0;
     CK(e, cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, e->device));
     const size_t slot_bytes = (size_t)rk_stage_bytes(qt, gs, kTileRows);

@@ -545,7 +545,7 @@ __device__ __forceinline__ void stage_pairs(const uint8_t* sp, int R, const uint
 // the keys, score exchange through L2 (tagged words), full softmax (redundantly per part), PV chains for HS/cph head dims.
 //
 // Everything that does not depend on the new token is requested BEFORE the q/k/v rows are polled: the part's K rows
-// (registers), its V column block (TMA bulk copies into a ring of 4 KB chunks, the V cache is stored in column blocks of
+// (registers), its V column block (TMA bulk copies into a ring of 16 KB chunks, the V cache is stored in column blocks of
 // HS/cph for exactly this) and the RoPE table row.  The two serial sections - softmax's sum and the PV chains - run
 // as register-double-buffered FP32 chains at ~5.5 cycles per dependent step.
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

@@ -1,5 +1,4 @@
 (timeout 300 python -m pytest tests -m gpu -x -q) > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log
-timeout 100 python profiles/phase_times.py 288 64 2>&1 > gpurun_out/phase288.log; head -1 gpurun_out/phase288.log
 timeout 300 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench.log 2>&1; python - <<EOP
 import json
 d=json.loads([l for l in open("gpurun_out/bench.log") if l.startswith("{")][-1])
