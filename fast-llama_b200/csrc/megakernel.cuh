@@ -331,8 +331,9 @@ __device__ __forceinline__ void quant_store(uint8_t* xq, float* xs, const float 
     uint32_t pk[PER / EPW];
 #pragma unroll
     for (int i = 0; i < PER; ++i) {
-        // (T)(y / sc) with a true IEEE division.  (A reciprocal-multiply fast path that falls back to the division near
-        // integers was measured SLOWER: some lane of a warp nearly always needs the fallback, so both paths execute.)
+        // (T)(y / sc) with a true IEEE division, inlined.  Measured alternatives, both slower: a reciprocal-multiply fast path
+        // with a fallback near integers (some lane nearly always needs the fallback), and a non-inlined helper per value / per
+        // 4 values (the calls cost more than the instruction-cache space they save).
         const uint32_t q = (uint32_t)cvtt_x86(__fdiv_rn(y[i], sc)) & ((QT == Q_INT8) ? 0xffu : 0xffffu);
         pk[i / EPW] = (i % EPW == 0) ? q : (pk[i / EPW] | (q << ((32 / EPW) * (i % EPW))));
     }
@@ -594,6 +595,7 @@ __device__ __forceinline__ float pv_rows(const float* vb, const float* wp, int D
         }
         if (i + 16 <= rows) { chain(va, wa, i); i += 16; }
     }
+#pragma unroll 1
     for (; i < rows; ++i) one(i);
     return o;
 }
@@ -758,6 +760,7 @@ __device__ __forceinline__ void attention_part(const MegaParams& p, uint8_t* sme
 
     // ---- softmax_sisd (tf_operators.cpp:176-186): max, expf(x - max), serial sum, divide
     float m = -INFINITY;
+#pragma unroll 1
     for (int t = tid; t < n; t += kConsumerThreads) m = fmaxf(m, att[t]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(kFull, m, o));
@@ -766,6 +769,7 @@ __device__ __forceinline__ void attention_part(const MegaParams& p, uint8_t* sme
     m = red[0];
 #pragma unroll
     for (int w = 1; w < kConsumerWarps; ++w) m = fmaxf(m, red[w]);
+#pragma unroll 1
     for (int t = tid; t < n; t += kConsumerThreads) att[t] = expf_exact(__fsub_rn(att[t], m));
     if (tid < 8) att[n + tid] = 0.0f;                      // the chains below read whole float4s
     consumer_sync();
@@ -783,11 +787,13 @@ __device__ __forceinline__ void attention_part(const MegaParams& p, uint8_t* sme
             sum = __fadd_rn(sum, c1.x); sum = __fadd_rn(sum, c1.y); sum = __fadd_rn(sum, c1.z); sum = __fadd_rn(sum, c1.w);
             c0 = n0; c1 = n1;
         }
+#pragma unroll 1
         for (int t = 4 * i; t < n; ++t) sum = __fadd_rn(sum, att[t]);
         red[16] = sum;
     }
     consumer_sync();
     const float sum = red[16];
+#pragma unroll 1
     for (int t = tid; t < n; t += kConsumerThreads) {
         const float w = __fdiv_rn(att[t], sum);
         att[t] = w;
