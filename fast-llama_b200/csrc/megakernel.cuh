@@ -7,10 +7,11 @@
 //   * warp 8 (one elected lane) is a TMA producer: it walks the token's static weight schedule and issues
 //     cp.async.bulk global->shared copies into a ring of stages guarded by full/empty mbarriers.  Weights do not
 //     depend on activations, so the producer runs ahead across phase, layer and token boundaries; only ring capacity
-//     (~180 KB per SM = ~4 us of this SM's HBM share) limits it.  A serial section shorter than that costs nothing.
+//     (~150 KB per SM = ~3.4 us of this SM's HBM share) limits it.  A serial section shorter than that costs nothing;
+//     a longer one cannot be caught up on (one SM ingests at most ~54 GB/s, and L2 bandwidth is no higher than HBM's).
 //   * warps 0-7 are consumers: per phase they (1) fetch the phase's input vector, (2) rebuild the quantised activation
-//     image in shared memory (rmsnorm chain, quantise), (3) drain their stages with the exact per-unit arithmetic of
-//     kernels.cuh and (4) publish their rows.
+//     image in shared memory (rmsnorm chain, quantise), (3) drain their stages into (scale product, dot) pairs;
+//     warp 9, the chain warp, turns the pairs into rows and publishes them (see the layout paragraph).
 //   * CTAs exchange activations as TAGGED WORDS (value, tag) written and read with single 8-byte accesses, tag = a
 //     number unique to (launch, token, layer, producer phase).  A reader issues all its loads at once and re-issues only
 //     those whose tag is stale, so "wait for every producer" and "fetch the vector" are ONE L2 round trip instead of
@@ -27,7 +28,7 @@
 // The 8 consumer warps share the K chunks of a tile round-robin: for its chunk a warp computes, for every row (lane), the
 // integer group dots (exact in any order) and the scale products, and drops the (product, float(dot)) pairs into a
 // shared-memory pair buffer.  The reference's FP32 chain over groups (quant_operators.cpp:274) is strictly sequential, so
-// a tenth warp - the CHAIN WARP - owns it: per superblock of 32 groups it waits on a named barrier for the 8 consumers,
+// a tenth warp - the CHAIN WARP - owns it: per superblock of 64 groups it waits on a named barrier for the 8 consumers,
 // walks  acc = fma(product, dot, acc)  for its 32 rows (4.5 cycles per group), and after the last superblock applies the
 // epilogue (store / residual add / SwiGLU / argmax) and publishes the rows.  Producer -> consumers -> chain warp is a
 // three-stage pipeline: the expensive part (loads + dp4a) never waits for the serial part.
@@ -38,7 +39,8 @@
 // Hardware facts that shape the code (all measured, see DESIGN.md "What the profiler taught us"):
 //   1. With ~227 KB of shared memory carved out there is practically no L1 left: every local-memory (stack) access and
 //      every re-read of a global word is an L2 round trip.  Nothing here may spill or take the address of a local.
-//   2. The kernel body must stay small (instruction cache): ONE instance of each phase routine inside a flat, rolled loop.
+//   2. The kernel body must stay small (instruction cache: 130 -> 96 KB of code was worth 4 %): ONE instance of each phase
+//      routine inside a flat, rolled loop; profiling counters and the event log are compiled in only with -DFL_PROFILE / -DFL_EVLOG.
 //   3. An L2 round trip costs 0.3 us on an idle chip and 1-1.5 us while the weight stream saturates HBM; dependent round
 //      trips are what a serial section is made of, so every one of them is counted.
 //   4. A consumer may only wait on a ring slot whose stage has already been issued: mbarrier waits are by phase PARITY, and
