@@ -1074,7 +1074,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
             pf.log(lane, warp, 8, pk);          // build starts
             {
                 const int K = (pk == 3) ? p.hidden : p.dim;
-                build_activation<QT, GS>(xq, xs, xt, misc, in, tag_in, gain, K, (pk == 4 && blockIdx.x == 0) ? p.tap_norm : nullptr, tid, pf);
+                if (!(p.debug_skip & 8)) build_activation<QT, GS>(xq, xs, xt, misc, in, tag_in, gain, K, (pk == 4 && blockIdx.x == 0) ? p.tap_norm : nullptr, tid, pf);
             }
             pf.stop(tid, 1);
             pf.log(lane, warp, 7, pk);          // drain starts
@@ -1180,7 +1180,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
                 }
                 consumer_sync();
             }
-            if (pk == 0 && attn_cta) {
+            if (pk == 0 && attn_cta && !(p.debug_skip & 8)) {
                 // ---- attention (transformer.cpp:136, :397-455)
                 consumer_sync();            // the V stage aliases the activation image the other warps may still be draining with
                 attention_part<HS>(p, smem, layer, my_head, my_part, pos, bs, tl + 1u, tl + 2u, tl + 3u, phases_drained, tid, pf);

@@ -1,7 +1,2 @@
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
 (timeout 300 python -m pytest tests -m gpu -x -q) > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log
-timeout 300 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench.log 2>&1; python - <<EOP
-import json
-d=json.loads([l for l in open("gpurun_out/bench.log") if l.startswith("{")][-1])
-print("BENCH", d["value"], d["ms_per_token"], d["e2e"]["value"], d["roofline"]["frac"])
-EOP
+for w in 3 6 99; do echo "== window $w"; FL_WINDOW=$w timeout 100 python profiles/phase_times.py 288 64 2>&1 | grep -E "ctx|ll_wait|attn_qkv|stage_wait|wait_first"; done
