@@ -9,10 +9,10 @@ The directory name has a hyphen (the repo's required layout); import it with
     import importlib.util, sys
     spec = importlib.util.spec_from_file_location("fast_llama_b200", ".../fast-llama_b200/__init__.py")
 """
-from .binding import (Engine, FlConfig, FlError, lib, lib_path, Q_INT8, Q_INT16,
+from .binding import (Engine, Sampler, FlConfig, FlError, lib, lib_path, Q_INT8, Q_INT16,
                       T_TOK_EMB, T_ATT_NORM, T_WQ, T_WK, T_WV, T_WO, T_FFN_NORM, T_W1, T_W2, T_W3, T_OUT_NORM, T_CLS,
                       FLAG_NO_GRAPH, FLAG_NO_PDL, FLAG_NO_MEGAKERNEL, FLAG_PROFILE, ops, EXPORTED_SYMBOLS)
 
 from . import shard, loaders
 
-__all__ = ["shard", "loaders", "Engine", "FlConfig", "FlError", "lib", "lib_path", "ops", "EXPORTED_SYMBOLS"]
+__all__ = ["shard", "loaders", "Engine", "Sampler", "FlConfig", "FlError", "lib", "lib_path", "ops", "EXPORTED_SYMBOLS"]

@@ -12,7 +12,8 @@ FLAG_NO_GRAPH, FLAG_NO_PDL, FLAG_NO_MEGAKERNEL, FLAG_PROFILE = 1, 2, 4, 8
 
 EXPORTED_SYMBOLS = [
     "fl_create", "fl_destroy", "fl_last_error", "fl_upload", "fl_finalize", "fl_forward", "fl_forward_batch",
-    "fl_generate_greedy", "fl_decode_async", "fl_stream", "fl_device_ptr", "fl_profile_read", "fl_sync", "fl_launch_count", "fl_step_bytes", "fl_tap",
+    "fl_generate_greedy", "fl_generate", "fl_sampler_create", "fl_sampler_destroy", "fl_sampler_sample", "fl_sampler_state",
+    "fl_decode_async", "fl_stream", "fl_device_ptr", "fl_profile_read", "fl_sync", "fl_launch_count", "fl_step_bytes", "fl_tap",
     "fl_set_comm", "fl_allgather_tokens", "fl_op_quantize", "fl_op_matmul_q", "fl_op_rmsnorm", "fl_op_rope",
     "fl_op_softmax", "fl_op_swiglu", "fl_op_expf", "fl_op_attn_decode", "fl_op_argmax",
 ]
@@ -80,6 +81,13 @@ def lib():
     L.fl_op_expf.argtypes = [vp, C.c_int, vp]
     L.fl_op_attn_decode.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]
     L.fl_op_argmax.argtypes = [vp, C.c_int, vp]
+    L.fl_generate.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_uint64, vp, i32p]
+    L.fl_sampler_create.argtypes = [C.c_int, C.c_uint64, C.POINTER(vp)]
+    L.fl_sampler_destroy.argtypes = [vp]
+    L.fl_sampler_destroy.restype = None
+    L.fl_sampler_sample.argtypes = [vp, vp, C.c_float, C.c_float, i32p]
+    L.fl_sampler_state.argtypes = [vp]
+    L.fl_sampler_state.restype = C.c_uint64
     _lib = L
     return L
 
@@ -224,6 +232,15 @@ class Engine:
         _check(lib().fl_generate_greedy(self.h, slot, _p(prompt), prompt.size, max_new, _p(out), C.byref(n)), self.h)
         return out[:n.value].copy()
 
+    def generate(self, prompt, max_new, temperature=1.0, topp=0.9, seed=0, slot=0):
+        """ParallelTransformer::generate (transformer.cpp:76-103) with its sampler; temperature 0 is generate_greedy."""
+        prompt = np.ascontiguousarray(prompt, np.int32)
+        out = np.zeros(max_new + 1, np.int32)
+        n = C.c_int32(0)
+        _check(lib().fl_generate(self.h, slot, _p(prompt), prompt.size, max_new, temperature, topp, seed, _p(out),
+                                 C.byref(n)), self.h)
+        return out[:n.value].copy()
+
     def decode_async(self, n_steps, slot=0):
         _check(lib().fl_decode_async(self.h, slot, n_steps), self.h)
 
@@ -259,3 +276,30 @@ class Engine:
         buf = np.empty(max(self.cfg.vocab_size, self.cfg.hidden_dim, 3 * self.cfg.dim), np.float32)
         n = _check(lib().fl_tap(self.h, name.encode(), _p(buf), buf.size), self.h)
         return buf[:n].copy()
+
+
+class Sampler:
+    """cpuft::Sampler (src/transformer/sampler.h:13-34): build(vocab_size, seed) / sample(logits, temperature, topp).
+    Host logic, as in the reference; `logits` (float32, vocab_size) is overwritten with the probabilities."""
+
+    def __init__(self, vocab_size, seed=0):
+        self.h = C.c_void_p()
+        self.n = vocab_size
+        _check(lib().fl_sampler_create(vocab_size, seed, C.byref(self.h)), None)
+
+    def sample(self, logits, temperature=1.0, topp=0.9):
+        assert logits.dtype == np.float32 and logits.size == self.n and logits.flags.c_contiguous
+        tok = C.c_int32(-1)
+        _check(lib().fl_sampler_sample(self.h, _p(logits), temperature, topp, C.byref(tok)), None)
+        return tok.value
+
+    @property
+    def state(self):
+        return lib().fl_sampler_state(self.h)
+
+    def close(self):
+        if self.h:
+            lib().fl_sampler_destroy(self.h)
+            self.h = C.c_void_p()
+
+    __del__ = close

@@ -846,6 +846,139 @@ int fl_generate_greedy(fl_engine* e, int seq_slot, const int32_t* prompt, int n_
     return FL_OK;
 }
 
+/* ---- temperature / top-p sampling (host logic, as in the reference) ------------------------------------------------------
+ * Sampler::sample (src/transformer/sampler.cpp:113-136) is host code in the reference and stays host code here: its softmax
+ * (src/blas/tf_operators.cpp:188-209) is one 32 000-long FP32 running sum whose order fixes the bits, so a device version
+ * would be a single-thread chain slower than the 128 KB logits copy it saves.  Greedy sampling (temperature 0, the path the
+ * benchmark times) never comes here: it is fused into the classifier phase on the device. */
+struct fl_sampler {
+    int n = 0;
+    uint64_t rng = 0;
+    struct Cand { float p; int id; };
+    std::vector<Cand> cand;
+};
+
+static int cand_order(const void* a, const void* b) {          // descending probability; ties compare equal (qsort decides)
+    const float x = static_cast<const fl_sampler::Cand*>(a)->p, y = static_cast<const fl_sampler::Cand*>(b)->p;
+    return (x < y) - (x > y);
+}
+
+static uint32_t xorshift_star(uint64_t& s) {                     // sampler.cpp:25-31
+    s ^= s >> 12;
+    s ^= s << 25;
+    s ^= s >> 27;
+    return (uint32_t)((s * 0x2545F4914F6CDD1Dull) >> 32);
+}
+
+// tf_operators.cpp:188-209.  libm expf is the reference's own; values more than 15 below the maximum are zeroed and left
+// out of the sum; the normaliser is a double reciprocal rounded to float (simd::multiply takes a float).
+static void sampler_softmax(float* x, int n) {
+    float top = x[0];
+    for (int i = 1; i < n; ++i) top = x[i] > top ? x[i] : top;
+    float step[16];
+    for (int i = 0; i < 16; ++i) step[i] = expf((float)(6 + i / 4));
+    float total = 0.0f;
+    for (int i = 0; i < n; ++i) {
+        const float d = x[i] - top;
+        float v = 0.0f;
+        if (!(d < -15)) {
+            v = d < 6.0 ? expf(d) : step[(int)((d - 6.0) * 4)];
+            total += v;
+        }
+        x[i] = v;
+    }
+    const float scale = (float)(1.0 / total);
+    for (int i = 0; i < n; ++i) x[i] *= scale;
+}
+
+int fl_sampler_create(int vocab_size, uint64_t seed, fl_sampler** out) {
+    if (!out || vocab_size < 2) return set_err(nullptr, FL_ERR_INVALID, "fl_sampler_create: bad argument");
+    fl_sampler* s = new fl_sampler();
+    s->n = vocab_size;
+    s->rng = seed;
+    s->cand.resize((size_t)vocab_size);
+    *out = s;
+    return FL_OK;
+}
+
+void fl_sampler_destroy(fl_sampler* s) { delete s; }
+
+uint64_t fl_sampler_state(const fl_sampler* s) { return s ? s->rng : 0; }
+
+int fl_sampler_sample(fl_sampler* s, float* logits, float temperature, float topp, int32_t* token_out) {
+    if (!s || !logits || !token_out) return set_err(nullptr, FL_ERR_INVALID, "fl_sampler_sample: null argument");
+    const int n = s->n;
+    if (temperature == 0.0f) {                                   // sampler.cpp:36-46; no random number is consumed
+        int best = 0;
+        for (int i = 1; i < n; ++i) if (logits[i] > logits[best]) best = i;
+        *token_out = best;
+        return FL_OK;
+    }
+    for (int i = 0; i < n; ++i) logits[i] /= temperature;
+    sampler_softmax(logits, n);
+    const float coin = (float)(xorshift_star(s->rng) >> 8) / 16777216.0f;
+    if (topp <= 0 || topp >= 1) {                                // sample_mult, sampler.cpp:48-59
+        float run = 0.0f;
+        int tok = n - 1;
+        for (int i = 0; i < n; ++i) {
+            run += logits[i];
+            if (coin < run) { tok = i; break; }
+        }
+        *token_out = tok;
+        return FL_OK;
+    }
+    // sample_topp, sampler.cpp:70-111: candidates at or above (1-topp)/(n-1), sorted, cut where the mass passes topp
+    const float least = (1.0f - topp) / (float)(n - 1);
+    int m = 0;
+    for (int i = 0; i < n; ++i)
+        if (logits[i] >= least) s->cand[(size_t)m++] = {logits[i], i};
+    qsort(s->cand.data(), (size_t)m, sizeof(fl_sampler::Cand), cand_order);
+    float mass = 0.0f;
+    int last = m - 1;
+    for (int i = 0; i < m; ++i) {
+        mass += s->cand[(size_t)i].p;
+        if (mass > topp) { last = i; break; }
+    }
+    const float r = coin * mass;
+    float run = 0.0f;
+    int tok = s->cand[(size_t)last].id;
+    for (int i = 0; i <= last; ++i) {
+        run += s->cand[(size_t)i].p;
+        if (r < run) { tok = s->cand[(size_t)i].id; break; }
+    }
+    *token_out = tok;
+    return FL_OK;
+}
+
+int fl_generate(fl_engine* e, int seq_slot, const int32_t* prompt, int n_prompt, int max_new, float temperature, float topp,
+                uint64_t seed, int32_t* out_tokens, int* n_out) {
+    if (!e || !prompt || !out_tokens || !n_out) return set_err(e, FL_ERR_INVALID, "fl_generate: null argument");
+    if (temperature == 0.0f) return fl_generate_greedy(e, seq_slot, prompt, n_prompt, max_new, out_tokens, n_out);
+    const fl_config& c = e->c;
+    if (n_prompt < 1 || n_prompt >= c.max_seq_len) return set_err(e, FL_ERR_INVALID, "fl_generate: prompt length %d not in [1, %d)", n_prompt, c.max_seq_len);
+    if (max_new > c.max_seq_len - n_prompt) max_new = c.max_seq_len - n_prompt;      // transformer.cpp:85-87
+    if (max_new < 0) max_new = 0;
+    fl_sampler* s = nullptr;
+    if (int rc = fl_sampler_create(c.vocab_size, seed, &s)) return rc;
+    std::vector<float> logits((size_t)c.vocab_size);
+    int n = 0, pos = 0, rc = FL_OK;
+    const int32_t* cur = prompt;
+    int n_cur = n_prompt;
+    int32_t tok = -1;
+    while (tok != 0 && pos < n_prompt + max_new) {               // transformer.cpp:93-101
+        rc = fl_forward(e, seq_slot, cur, n_cur, pos, logits.data(), nullptr);
+        if (rc) break;
+        fl_sampler_sample(s, logits.data(), temperature, topp, &tok);
+        out_tokens[n++] = tok;
+        pos += n_cur;
+        cur = &tok;
+        n_cur = 1;
+    }
+    fl_sampler_destroy(s);
+    *n_out = n;
+    return rc;
+}
+
 void* fl_stream(fl_engine* e) { return e ? (void*)e->stream : nullptr; }
 
 int fl_sync(fl_engine* e) {

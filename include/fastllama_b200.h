@@ -109,6 +109,21 @@ int  fl_forward_batch(fl_engine* e, int n_seqs, const int32_t* tokens, const int
 int  fl_generate_greedy(fl_engine* e, int seq_slot, const int32_t* prompt, int n_prompt, int max_new,
                         int32_t* out_tokens, int* n_out);
 
+/* generate() with the reference's sampler (src/transformer/transformer.cpp:76-103 + src/transformer/sampler.cpp:113-136):
+ * temperature 0 is fl_generate_greedy (device-resident); otherwise each step reads the logits back and samples on the
+ * host with the reference's arithmetic (temperature divide, its softmax, xorshift* coin, multinomial or top-p with
+ * qsort order), seeded like Sampler::build(vocab, seed).  Same stop rule and clipping as fl_generate_greedy. */
+int  fl_generate(fl_engine* e, int seq_slot, const int32_t* prompt, int n_prompt, int max_new, float temperature,
+                 float topp, uint64_t seed, int32_t* out_tokens, int* n_out);
+
+/* The sampler on its own (replaces cpuft::Sampler, src/transformer/sampler.h:13-34).  `logits` is a HOST buffer of
+ * vocab_size floats and is overwritten with the probabilities, as the reference does. */
+typedef struct fl_sampler fl_sampler;
+int      fl_sampler_create(int vocab_size, uint64_t seed, fl_sampler** out);
+void     fl_sampler_destroy(fl_sampler* s);
+int      fl_sampler_sample(fl_sampler* s, float* logits, float temperature, float topp, int32_t* token_out);
+uint64_t fl_sampler_state(const fl_sampler* s);
+
 /* Device-resident decode for measurement: runs n_steps greedy steps starting from the current device
  * state of `seq_slot` (set by a previous fl_forward / fl_generate_greedy), asynchronously on the engine
  * stream.  fl_stream() exposes that stream (a cudaStream_t) so the caller can bracket it with events. */

@@ -216,6 +216,33 @@ int ref_generate_greedy(void* h, const int* prompt, int n_prompt, int max_new, i
     return n;
 }
 
+/* The reference's Sampler itself (sampler.cpp:113-136) on a caller-owned logits buffer, which it rewrites in place
+ * (temperature divide + softmax) exactly as generate() lets it.  *rng is the xorshift state (sampler.cpp:25-34):
+ * read before, written back after, so a sequence of calls reproduces one Sampler instance. */
+int ref_sampler_sample(float* logits, int n, float temperature, float topp, uint64_t* rng) {
+    cpuft::Sampler s;
+    s.build(n, *rng);
+    cpuft::Tensor t = cpuft::Tensor::manage(logits, n);
+    int tok = s.sample(t, temperature, topp);
+    *rng = s._rng_state;
+    return tok;
+}
+
+/* generate() with sampling through the reference's public API (transformer.cpp:76-103); the sampler is re-seeded first
+ * (ParallelTransformer::load seeds it at :40). */
+int ref_generate(void* h, const int* prompt, int n_prompt, int max_new, float temperature, float topp,
+                 uint64_t seed, int* out, int out_cap) {
+    auto& pt = static_cast<RefModel*>(h)->pt;
+    pt._sampler._rng_state = seed;
+    std::vector<int> in(prompt, prompt + n_prompt);
+    int n = 0;
+    pt.generate(in, [&](std::span<const int> toks, int, bool) -> bool {
+        if (n < out_cap) out[n++] = toks[0];
+        return n < out_cap;
+    }, max_new, temperature, topp);
+    return n;
+}
+
 int ref_encode(void* h, const char* text, int* out, int cap) {
     auto v = static_cast<RefModel*>(h)->pt.encode(text);
     int n = int(v.size()) < cap ? int(v.size()) : cap;

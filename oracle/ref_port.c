@@ -283,6 +283,66 @@ int port_argmax(const float* logits, int n) {
 }
 
 /* ------------------------------------------------------------------------------------------- */
+/* Sampler — src/transformer/sampler.cpp:25-136 with the softmax it calls (src/blas/tf_operators.cpp */
+/* :188-209, NOT the attention's softmax_sisd): logits /= T; p = softmax; coin = xorshift* >> 8 /2^24; */
+/* topp outside (0,1): first index whose running sum exceeds coin; else nucleus sampling over the     */
+/* candidates p >= (1-topp)/(n-1), sorted by libc qsort (same comparator => same order on ties).     */
+/* ------------------------------------------------------------------------------------------- */
+void port_softmax(float* x, size_t n) {
+    float mx = x[0];
+    for (size_t i = 1; i < n; ++i) if (x[i] > mx) mx = x[i];          /* array_max: order-free */
+    float big[16];
+    for (int i = 0; i < 16; ++i) big[i] = expf((float)(6 + i / 4));   /* :192-194, integer i/4 */
+    float sum = 0.0f;
+    for (size_t i = 0; i < n; ++i) {
+        float d = x[i] - mx;
+        if (d < -15) { x[i] = 0.0f; continue; }                        /* dropped AND not summed */
+        x[i] = d < 6.0 ? expf(d) : big[(int)((d - 6.0) * 4)];
+        sum += x[i];
+    }
+    float inv = (float)(1.0 / sum);                                    /* double division, then float (simd.h:51) */
+    for (size_t i = 0; i < n; ++i) x[i] *= inv;
+}
+
+uint32_t port_random_u32(uint64_t* st) {
+    uint64_t s = *st;
+    s ^= s >> 12; s ^= s << 25; s ^= s >> 27;
+    *st = s;
+    return (uint32_t)((s * 0x2545F4914F6CDD1Dull) >> 32);
+}
+
+typedef struct { float p; int id; } port_cand;
+static int cand_desc(const void* a, const void* b) {
+    float pa = ((const port_cand*)a)->p, pb = ((const port_cand*)b)->p;
+    return pa > pb ? -1 : (pa < pb ? 1 : 0);
+}
+
+int port_sample(float* logits, int n, float temperature, float topp, uint64_t* rng) {
+    if (temperature == 0.0f) return port_argmax(logits, n);            /* no coin is drawn */
+    for (int i = 0; i < n; ++i) logits[i] /= temperature;
+    port_softmax(logits, (size_t)n);
+    float coin = (float)(port_random_u32(rng) >> 8) / 16777216.0f;
+    if (topp <= 0 || topp >= 1) {                                      /* sample_mult :48-59 */
+        float run = 0.0f;
+        for (int i = 0; i < n; ++i) { run += logits[i]; if (coin < run) return i; }
+        return n - 1;
+    }
+    port_cand* c = (port_cand*)malloc(sizeof(port_cand) * (size_t)n);  /* sample_topp :70-111 */
+    float floor_p = (1.0f - topp) / (float)(n - 1);
+    int m = 0;
+    for (int i = 0; i < n; ++i) if (logits[i] >= floor_p) { c[m].p = logits[i]; c[m].id = i; ++m; }
+    qsort(c, (size_t)m, sizeof(port_cand), cand_desc);
+    float mass = 0.0f;
+    int last = m - 1;
+    for (int i = 0; i < m; ++i) { mass += c[i].p; if (mass > topp) { last = i; break; } }
+    float r = coin * mass, run = 0.0f;
+    int tok = c[last].id;
+    for (int i = 0; i <= last; ++i) { run += c[i].p; if (r < run) { tok = c[i].id; break; } }
+    free(c);
+    return tok;
+}
+
+/* ------------------------------------------------------------------------------------------- */
 /* whole model: ParallelTransformer::forward — src/transformer/transformer.cpp:105-161 and the     */
 /* six task bodies :386-505.  Row/head partitioning across worker threads has no cross-thread      */
 /* reduction, so a single-threaded restatement is bit-identical for any -j.                        */

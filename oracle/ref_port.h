@@ -38,6 +38,9 @@ void  port_weighted_sum(float* out, const float* matrix, const float* weights, i
 void  port_swiglu(float* xo, const float* xr, size_t n);
 float port_expf_emul(float x);      /* the double-precision algorithm the CUDA kernels run; must equal libm expf */
 int   port_argmax(const float* logits, int n);
+void  port_softmax(float* x, size_t n);                /* the sampler's softmax, tf_operators.cpp:188-209 */
+uint32_t port_random_u32(uint64_t* state);
+int   port_sample(float* logits, int n, float temperature, float topp, uint64_t* rng);   /* rewrites logits */
 
 /* whole model */
 typedef struct port_model port_model;

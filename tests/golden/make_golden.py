@@ -21,6 +21,41 @@ from fixtures import TINY, gen_weights, write_llama2c, write_tokenizer_bin, synt
 import golden_inputs as gi  # noqa: E402
 
 
+def sampler_golden(R):
+    """Sampler::sample (sampler.cpp:113-136) and generate() with sampling (transformer.cpp:76-103) from the real reference."""
+    import ctypes as C
+    out = {}
+    for name, logits in gi.sampler_inputs():
+        for ci, (temp, topp, seed) in enumerate(gi.SAMPLER_CASES):
+            rng = C.c_uint64(seed)
+            toks = []
+            for d in range(gi.SAMPLER_DRAWS):
+                buf = logits.copy()
+                toks.append(R.ref_sampler_sample(ptr(buf), buf.size, temp, topp, C.byref(rng)))
+                if d == 0 and temp != 0.0:                     # the probabilities the reference's softmax left behind:
+                    if ci == 0 and buf.size <= 8000:          # in full for the small inputs, as a bit checksum otherwise
+                        out[f"probs_{name}_{ci}"] = buf
+                    out[f"probsum_{name}_{ci}"] = gi.bits_checksum(buf)
+            out[f"tokens_{name}_{ci}"] = np.array(toks, np.int32)
+            out[f"state_{name}_{ci}"] = np.uint64(rng.value)
+    spec = TINY
+    w = gen_weights(spec, 1)
+    with tempfile.TemporaryDirectory() as d:
+        write_llama2c(d + "/model.bin", spec, w)
+        write_tokenizer_bin(d + "/tok.bin", synthetic_vocab(spec.vocab_size))
+        h = R.ref_model_load((d + "/model.bin").encode(), (d + "/tok.bin").encode(), 3, Q_INT8, 2, 64, 0)
+        assert h
+        prompt = prompt_tokens(spec, 6, seed=3)
+        for gi_, (temp, topp, seed) in enumerate([(0.9, 0.9, 1234), (1.0, 1.0, 99), (0.6, 0.8, 5)]):
+            gen = np.zeros(64, np.int32)
+            n = R.ref_generate(h, ptr(prompt), prompt.size, 40, temp, topp, seed, ptr(gen), 64)
+            out[f"generate_{gi_}"] = gen[:n].copy()
+            out[f"generate_{gi_}_args"] = np.array([temp, topp, seed], np.float64)
+        R.ref_model_free(h)
+    out["prompt"] = prompt
+    np.savez_compressed(os.path.join(HERE, "sampler_golden.npz"), **out)
+
+
 def main():
     R = ref()
     assert R is not None, "build oracle/_ref first (bash oracle/build_ref.sh)"
@@ -83,6 +118,7 @@ def main():
         R.ref_model_free(h)
     np.savez_compressed(os.path.join(HERE, "tiny_model_logits.npz"), seed=seed, prompt=prompt, prefill_logits=prefill,
                         decode_tokens=np.array(toks, np.int32), decode_logits=np.stack(dl), generate_tokens=gen[:n])
+    sampler_golden(R)
     print("golden vectors written:", len(out), "op arrays;", "generate ->", gen[:n].tolist())
 
 

@@ -67,3 +67,27 @@ def swiglu_inputs():
     rng = np.random.default_rng(107)
     for n in (8, 2048, 11008):
         yield f"n{n}", (rng.standard_normal(n) * 4).astype(np.float32), rng.standard_normal(n).astype(np.float32)
+
+
+def sampler_inputs():
+    """(name, logits) for Sampler::sample: a peaked and a flat distribution at a real vocabulary size, a small one, and one
+    with many exactly equal logits (so that the candidate sort sees ties)."""
+    r = np.random.default_rng(77)
+    peaked = (r.standard_normal(32000) * 3.0).astype(np.float32)
+    flat = (r.standard_normal(32000) * 0.3).astype(np.float32)
+    small = (r.standard_normal(1000) * 2.0).astype(np.float32)
+    ties = (np.round(r.standard_normal(4096) * 2.0) * 0.5).astype(np.float32)
+    wide = (r.standard_normal(8000) * 12.0).astype(np.float32)        # many entries more than 15 below the maximum
+    return [("peaked", peaked), ("flat", flat), ("small", small), ("ties", ties), ("wide", wide)]
+
+
+# (temperature, topp, seed): nucleus sampling, plain multinomial (topp outside (0,1)), greedy
+SAMPLER_CASES = [(1.0, 0.9, 1), (0.7, 0.95, 2), (1.3, 0.5, 3), (1.0, 1.0, 4), (0.5, 0.0, 5), (2.0, 0.99, 6), (0.0, 0.9, 7)]
+SAMPLER_DRAWS = 6
+
+
+def bits_checksum(a):
+    """order-sensitive checksum of the bit patterns of a float32 array (two uint64 words)"""
+    b = np.ascontiguousarray(a, np.float32).view(np.uint32).astype(np.uint64)
+    k = np.arange(1, b.size + 1, dtype=np.uint64)
+    return np.array([np.bitwise_xor.reduce(b * k), (b * (k | np.uint64(1))).sum(dtype=np.uint64)], np.uint64)

@@ -60,6 +60,8 @@ def port():
     lib.port_expf_emul.argtypes = [C.c_float]
     lib.port_expf_emul.restype = C.c_float
     lib.port_argmax.argtypes = [vp, C.c_int]
+    lib.port_softmax.argtypes = [vp, C.c_size_t]
+    lib.port_sample.argtypes = [vp, C.c_int, C.c_float, C.c_float, C.POINTER(C.c_uint64)]
     lib.port_model_create.argtypes = [C.POINTER(PortConfig)]
     lib.port_model_create.restype = vp
     lib.port_model_free.argtypes = [vp]
@@ -97,6 +99,8 @@ def _load_ref(name):
     lib.ref_add.argtypes = [vp, vp, C.c_size_t]
     lib.ref_simd_size.restype = C.c_size_t
     lib.ref_sample_argmax.argtypes = [vp, C.c_int]
+    lib.ref_sampler_sample.argtypes = [vp, C.c_int, C.c_float, C.c_float, C.POINTER(C.c_uint64)]
+    lib.ref_generate.argtypes = [vp, vp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_uint64, vp, C.c_int]
     lib.ref_model_load.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     lib.ref_model_load.restype = vp
     lib.ref_model_free.argtypes = [vp]
