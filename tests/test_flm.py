@@ -1,0 +1,186 @@
+"""The .flm model file (tools/convert_flm.py:465-748,1075-1172; src/model_loaders/flm_loader.cpp).
+
+CPU: our writer reproduces, byte for byte, a file the reference CONVERTER's own classes wrote (tests/golden/micro_int8.flm);
+our reader recovers the seeded tensors, config and vocabulary from it; the numpy quantiser equals the converter's; and, when
+oracle/_ref is present, the reference's C++ loader accepts a file from our writer and its forward() equals the oracle on the
+tensors our reader returns.  GPU: engine_from_flm on such a file gives the logits the reference's C++ produced from the same
+bytes (tests/golden/flm_golden.npz)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import flm_inputs as fi
+from oracle_libs import port, ref, ptr, bits, PortConfig, Q_INT8, Q_INT16
+from fixtures import TINY, gen_weights, prompt_tokens
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+MICRO_FLM = os.path.join(HERE, "golden", "micro_int8.flm")
+FLM_GOLDEN = os.path.join(HERE, "golden", "flm_golden.npz")
+
+
+def test_writer_reproduces_the_reference_converters_file_byte_for_byte(fl, tmp_path):
+    spec = fi.MICRO
+    w = gen_weights(spec, seed=21)
+    p = tmp_path / "micro.flm"
+    fl.flm.write_flm(p, fi.config_of(spec, Q_INT8, 64, "micro"), fi.quantized_tensors(fl, spec, w, Q_INT8, 64),
+                     fi.micro_vocab(spec.vocab_size))
+    ours, theirs = p.read_bytes(), open(MICRO_FLM, "rb").read()
+    assert len(ours) == len(theirs)
+    assert ours == theirs, next(i for i, (a, b) in enumerate(zip(ours, theirs)) if a != b)
+
+
+def test_reader_recovers_config_tensors_and_vocabulary(fl):
+    spec = fi.MICRO
+    cfg, t, vocab = fl.flm.read_flm(MICRO_FLM)
+    want_cfg = fi.config_of(spec, Q_INT8, 64, "micro")
+    for k, v in want_cfg.items():
+        if isinstance(v, float):
+            assert np.float32(cfg[k]) == np.float32(v), k
+        else:
+            assert cfg[k] == v, k
+    assert cfg["version"] == (1, 0, 0)
+    want = fi.quantized_tensors(fl, spec, gen_weights(spec, seed=21), Q_INT8, 64)
+    assert set(t) == set(want)
+    for key, (q, s) in want.items():
+        gq, gs = t[key]
+        assert gq.dtype == q.dtype and gq.shape == q.shape and np.array_equal(gq, q), key
+        assert (gs is None) == (s is None), key
+        if s is not None:
+            assert gs.shape == s.shape and np.array_equal(bits(np.ascontiguousarray(gs)), bits(s)), key
+    v = fi.micro_vocab(spec.vocab_size)
+    assert vocab["texts"] == v["texts"] and vocab["types"] == v["types"] and vocab["special"] == v["special"]
+    assert vocab["scores"] == v["scores"] and vocab["vocab_type"] == 2 and vocab["conn_tag"] == "▁"
+    assert vocab["show"][3] == " w0" and vocab["show"][4] == "p1"          # ▁-pieces are shown with a leading space
+
+
+def test_int16_and_gqa_round_trip(fl, tmp_path):
+    from test_forward_gpu import GQA
+    for spec, qt, gs in ((GQA, Q_INT16, 64), (fi.MICRO, Q_INT8, 32)):
+        w = gen_weights(spec, seed=5)
+        t = fi.quantized_tensors(fl, spec, w, qt, gs)
+        p = tmp_path / "m.flm"
+        fl.flm.write_flm(p, fi.config_of(spec, qt, gs, "x"), t, None)
+        cfg, got, vocab = fl.flm.read_flm(p)
+        assert vocab is None and cfg["quant_type"] == qt and cfg["quant_group_size"] == gs
+        assert cfg["n_kv_heads"] == spec.n_kv_heads
+        for key, (q, s) in t.items():
+            assert np.array_equal(got[key][0], q), key
+            if s is not None:
+                assert np.array_equal(bits(np.ascontiguousarray(got[key][1])), bits(s)), key
+
+
+def test_permute_qk_is_the_converters_row_order(fl):
+    # HF layout: per head [first rotary half | second half]; the reference's RoPE pairs rows (2i, 2i+1)
+    n_heads, hs, cols = 4, 8, 3
+    w = np.arange(n_heads * hs * cols, dtype=np.float32).reshape(n_heads * hs, cols)
+    p = fl.flm.permute_qk(w, n_heads)
+    for h in range(n_heads):
+        for i in range(hs // 2):
+            assert np.array_equal(p[h * hs + 2 * i], w[h * hs + i])
+            assert np.array_equal(p[h * hs + 2 * i + 1], w[h * hs + hs // 2 + i])
+    wk = w[:2 * hs]
+    assert np.array_equal(fl.flm.permute_qk(wk, n_heads, 2), fl.flm.permute_qk(wk, 2))
+
+
+def test_malformed_files_are_rejected(fl, tmp_path):
+    data = open(MICRO_FLM, "rb").read()
+    bad = tmp_path / "bad.flm"
+    bad.write_bytes(b"\0\0\0\0" + data[4:])
+    with pytest.raises(fl.flm.FlmError):
+        fl.flm.read_flm(bad)
+    bad.write_bytes(data[:len(data) // 2])                       # truncated inside a tensor
+    with pytest.raises(fl.flm.FlmError):
+        fl.flm.read_flm(bad)
+    bad.write_bytes(data[:6])
+    with pytest.raises(fl.flm.FlmError):
+        fl.flm.read_flm(bad)
+
+
+def tiny_flm(fl, path):
+    spec = TINY
+    w = gen_weights(spec, seed=1)
+    fl.flm.write_flm(path, fi.config_of(spec, Q_INT8, 64, "tiny"), fi.quantized_tensors(fl, spec, w, Q_INT8, 64),
+                     fi.micro_vocab(spec.vocab_size))
+    return spec
+
+
+def port_model_from_flm(fl, path):
+    cfg, t, _ = fl.flm.read_flm(path)
+    P = port()
+    pc = PortConfig(cfg["dim"], cfg["hidden_dim"], cfg["n_layers"], cfg["n_heads"], cfg["n_kv_heads"],
+                    cfg["dim"] // cfg["n_heads"], cfg["vocab_size"], 1024, cfg["quant_type"], cfg["quant_group_size"])
+    pm = P.port_model_create(C.byref(pc))
+    for (k, l), (q, s) in t.items():
+        q = np.ascontiguousarray(q)
+        s = None if s is None else np.ascontiguousarray(s)
+        rows = q.shape[0] if q.ndim == 2 else 1
+        assert P.port_model_set_tensor(pm, k, l, ptr(q), ptr(s) if s is not None else None, rows, q.shape[-1]) == 0
+    return pm, cfg
+
+
+def test_oracle_on_our_reader_matches_reference_golden_logits(fl, tmp_path):
+    """reference C++ (load_flm + forward) on the file == oracle on what our reader returns for the same file"""
+    p = tmp_path / "tiny.flm"
+    spec = tiny_flm(fl, p)
+    g = np.load(FLM_GOLDEN)
+    pm, cfg = port_model_from_flm(fl, p)
+    P = port()
+    logits = np.empty(spec.vocab_size, np.float32)
+    prompt = g["prompt"].astype(np.int32)
+    P.port_forward(pm, ptr(prompt), prompt.size, 0, ptr(logits))
+    assert np.array_equal(bits(logits), bits(g["prefill_logits"]))
+    pos = prompt.size
+    for i, tok in enumerate(g["decode_tokens"]):
+        t = np.array([tok], np.int32)
+        P.port_forward(pm, ptr(t), 1, pos, ptr(logits))
+        assert np.array_equal(bits(logits), bits(g["decode_logits"][i])), i
+        pos += 1
+    P.port_model_free(pm)
+
+
+def test_reference_loader_accepts_our_file_live(fl, tmp_path):
+    R = ref()
+    if R is None:
+        pytest.skip("oracle/_ref not built (GPU box): covered by tests/golden/flm_golden.npz")
+    # multi-head only: the reference's own grouped-query path leaves all but the first query head of a group unset
+    # (Tensor::weighted_sum passes out.rows() instead of total_rows(), tensor.cpp:713; DESIGN.md defect D10)
+    from fixtures import TINY64
+    spec, qt, gs = TINY64, Q_INT8, 64
+    w = gen_weights(spec, seed=8)
+    p = tmp_path / "tiny64.flm"
+    fl.flm.write_flm(p, fi.config_of(spec, qt, gs, "tiny64"), fi.quantized_tensors(fl, spec, w, qt, gs),
+                     fi.micro_vocab(spec.vocab_size))
+    h = R.ref_model_load(str(p).encode(), b"", 1, qt, 2, 64, 0)
+    assert h
+    cfgv = (C.c_int * 10)()
+    R.ref_model_config(h, cfgv)
+    assert list(cfgv)[:7] == [spec.dim, spec.hidden_dim, spec.n_layers, spec.n_heads, spec.n_kv_heads, spec.head_size, spec.vocab_size]
+    pm, _ = port_model_from_flm(fl, p)
+    P = port()
+    prompt = prompt_tokens(spec, 5, seed=2)
+    a, b = np.empty(spec.vocab_size, np.float32), np.empty(spec.vocab_size, np.float32)
+    R.ref_forward(h, ptr(prompt), prompt.size, 0, ptr(a))
+    P.port_forward(pm, ptr(prompt), prompt.size, 0, ptr(b))
+    assert np.array_equal(bits(a), bits(b))
+    R.ref_model_free(h)
+    P.port_model_free(pm)
+
+
+@pytest.mark.gpu
+def test_engine_from_flm_matches_reference_golden_logits(fl, tmp_path):
+    p = tmp_path / "tiny.flm"
+    spec = tiny_flm(fl, p)
+    g = np.load(FLM_GOLDEN)
+    eng, cfg, vocab = fl.flm.engine_from_flm(p)
+    assert cfg["dim"] == spec.dim and len(vocab["texts"]) == spec.vocab_size
+    prompt = g["prompt"].astype(np.int32)
+    got = eng.forward(prompt, 0)
+    assert np.array_equal(bits(got), bits(g["prefill_logits"]))
+    pos = prompt.size
+    for i, tok in enumerate(g["decode_tokens"]):
+        got = eng.forward(np.array([tok], np.int32), pos)
+        assert np.array_equal(bits(got), bits(g["decode_logits"][i])), i
+        pos += 1
+    eng.close()

@@ -1,6 +1,7 @@
 """GPU parity, model level: fl_forward / fl_generate_greedy (through the C-ABI) against the CPU oracle's forward()
 on the same seeded weights and token ids.  Logits must be BIT-identical (so greedy token ids are identical too),
-for INT8 and INT16, group 64 and 32, MHA and GQA.  Golden logits generated from the real reference
+for INT8 and INT16, group 64 and 32, MHA and GQA (GQA against the oracle only: the reference's own grouped-query path
+is broken, DESIGN.md defect D10).  Golden logits generated from the real reference
 (tests/golden/make_golden.py) are checked as well, so the chain GPU == port == reference is closed on the GPU box
 where /root/reference does not exist."""
 import ctypes as C
