@@ -1,2 +1,1 @@
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 2 --warmup 3 > gpurun_out/bench_n2.log 2>&1
-tail -c 1500 gpurun_out/bench_n2.log
+python -m pytest tests -m gpu -x -q 2>&1 | tail -6 > gpurun_out/pytest_gpu_r01_final.log; cat gpurun_out/pytest_gpu_r01_final.log
