@@ -412,10 +412,11 @@ __device__ __forceinline__ void build_activation(uint8_t* xq, float* xs, float* 
     const int G = K / GS;
     const int sub = tid & 7, g0 = tid >> 3;
     const int n_pass = ceil_div(G, GPP);
-#pragma unroll 1
-    for (int b0 = 0; b0 < n_pass; b0 += MAXP) {
-        uint4 w[MAXP][LPP];
-        float4 gw[MAXP][PER / 4];
+    uint4 w[MAXP][LPP];
+    float4 gw[MAXP][PER / 4];
+    // all loads of a batch are issued before the first tag is looked at; the NEXT batch's loads are issued as soon as this
+    // batch's values have left `w`, so their round trip overlaps this batch's quantisation (hd needs two batches)
+    auto issue_batch = [&](int b0) {
 #pragma unroll
         for (int ps = 0; ps < MAXP; ++ps) {
             const int g = g0 + (b0 + ps) * GPP;
@@ -429,6 +430,10 @@ __device__ __forceinline__ void build_activation(uint8_t* xq, float* xs, float* 
                 }
             }
         }
+    };
+    issue_batch(0);
+#pragma unroll 1
+    for (int b0 = 0; b0 < n_pass; b0 += MAXP) {
         bool again;
         do {
             again = false;
@@ -461,6 +466,7 @@ __device__ __forceinline__ void build_activation(uint8_t* xq, float* xs, float* 
 #pragma unroll
             for (int q = 0; q < LPP; ++q) { y[ps][2 * q] = __uint_as_float(w[ps][q].x); y[ps][2 * q + 1] = __uint_as_float(w[ps][q].z); }
         }
+        if (!gain && b0 + MAXP < n_pass) issue_batch(b0 + MAXP);
         float rr = 1.0f;
         if (gain) {
             // raw x -> transposed image for the chain; products and group maxima stay in registers
