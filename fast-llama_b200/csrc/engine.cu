@@ -92,7 +92,9 @@ struct fl_engine {
     bool use_mega = false;
     int cph = 1;                        // CTAs per head in the persistent kernel; also the column blocking of the V cache
     MegaLayer* mega_layers = nullptr;
-    uint2 *x1t = nullptr, *qkvt = nullptr, *attnt = nullptr, *hdt = nullptr, *score_t = nullptr;   // tagged exchange buffers
+    uint2 *x1t = nullptr, *qkvt = nullptr, *attnt = nullptr, *hdt = nullptr, *score_t = nullptr;   // tagged exchange buffers (sequence 0)
+    uint8_t* xchg = nullptr;          // one block per sequence slot: [x1t | qkvt | attnt | hdt | score_t | am], xchg_stride bytes apart
+    size_t xchg_stride = 0;
     uint4* am = nullptr;
     uint32_t epoch = 0;                 // last tag handed out (see megakernel.cuh)
     unsigned long long* prof = nullptr;
@@ -329,14 +331,18 @@ int enqueue_step(fl_engine* e, int slot, cudaStream_t st, int* n_kernels) {
     return FL_OK;
 }
 
+// multi = true: the variant that walks several sequences per phase (fl_forward_batch)
 template <typename F>
-int dispatch_mega(int qt, int gs, int hs, F&& f) {
-    if (qt == FL_Q_INT8 && gs == 64 && hs == 128) return f(decode_megakernel<Q_INT8, 64, 128>);
-    if (qt == FL_Q_INT8 && gs == 64 && hs == 64) return f(decode_megakernel<Q_INT8, 64, 64>);
-    if (qt == FL_Q_INT8 && gs == 32 && hs == 128) return f(decode_megakernel<Q_INT8, 32, 128>);
-    if (qt == FL_Q_INT8 && gs == 32 && hs == 64) return f(decode_megakernel<Q_INT8, 32, 64>);
-    if (qt == FL_Q_INT16 && gs == 64 && hs == 128) return f(decode_megakernel<Q_INT16, 64, 128>);
-    if (qt == FL_Q_INT16 && gs == 64 && hs == 64) return f(decode_megakernel<Q_INT16, 64, 64>);
+int dispatch_mega(int qt, int gs, int hs, bool multi, F&& f) {
+#define FL_MEGA_CASE(QT_, QTC, GS_, HS_) \
+    if (qt == QT_ && gs == GS_ && hs == HS_) return multi ? f(decode_megakernel<QTC, GS_, HS_, true>) : f(decode_megakernel<QTC, GS_, HS_, false>);
+    FL_MEGA_CASE(FL_Q_INT8, Q_INT8, 64, 128)
+    FL_MEGA_CASE(FL_Q_INT8, Q_INT8, 64, 64)
+    FL_MEGA_CASE(FL_Q_INT8, Q_INT8, 32, 128)
+    FL_MEGA_CASE(FL_Q_INT8, Q_INT8, 32, 64)
+    FL_MEGA_CASE(FL_Q_INT16, Q_INT16, 64, 128)
+    FL_MEGA_CASE(FL_Q_INT16, Q_INT16, 64, 64)
+#undef FL_MEGA_CASE
     return FL_ERR_UNSUPPORTED;
 }
 
@@ -354,18 +360,20 @@ int setup_mega(fl_engine* e) {
     CK(e, cudaStreamSynchronize(e->stream));
     const int qkv_rows = c.dim + 2 * c.head_size * c.n_kv_heads;
     const int score_stride = (c.max_seq_len + 3) & ~1;
-    auto alloc_tagged = [&](uint2** ptr, size_t words) -> int {
-        CK(e, cudaMalloc(ptr, (words + 2) * sizeof(uint2)));
-        CK(e, cudaMemsetAsync(*ptr, 0, (words + 2) * sizeof(uint2), e->stream));      // tag 0 is never used
-        return FL_OK;
-    };
-    if (int rc = alloc_tagged(&e->x1t, c.dim)) return rc;
-    if (int rc = alloc_tagged(&e->qkvt, qkv_rows)) return rc;
-    if (int rc = alloc_tagged(&e->attnt, c.dim)) return rc;
-    if (int rc = alloc_tagged(&e->hdt, c.hidden_dim)) return rc;
-    if (int rc = alloc_tagged(&e->score_t, (size_t)c.n_heads * score_stride)) return rc;
-    CK(e, cudaMalloc(&e->am, sizeof(uint4) * e->n_sms));
-    CK(e, cudaMemsetAsync(e->am, 0, sizeof(uint4) * e->n_sms, e->stream));
+    {
+        // exchange buffers: one block per sequence slot, the same layout in each (MegaParams::xchg_stride)
+        size_t off = 0;
+        auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+        const size_t o_x1 = take((c.dim + 2) * sizeof(uint2)), o_qkv = take((qkv_rows + 2) * sizeof(uint2));
+        const size_t o_attn = take((c.dim + 2) * sizeof(uint2)), o_hd = take((c.hidden_dim + 2) * sizeof(uint2));
+        const size_t o_sc = take(((size_t)c.n_heads * score_stride + 2) * sizeof(uint2)), o_am = take(sizeof(uint4) * e->n_sms);
+        e->xchg_stride = off;
+        CK(e, cudaMalloc(&e->xchg, off * c.max_seqs));
+        CK(e, cudaMemsetAsync(e->xchg, 0, off * c.max_seqs, e->stream));      // tag 0 is never used
+        e->x1t = reinterpret_cast<uint2*>(e->xchg + o_x1); e->qkvt = reinterpret_cast<uint2*>(e->xchg + o_qkv);
+        e->attnt = reinterpret_cast<uint2*>(e->xchg + o_attn); e->hdt = reinterpret_cast<uint2*>(e->xchg + o_hd);
+        e->score_t = reinterpret_cast<uint2*>(e->xchg + o_sc); e->am = reinterpret_cast<uint4*>(e->xchg + o_am);
+    }
     CK(e, cudaMalloc(&e->prof, sizeof(unsigned long long) * 32 * e->n_sms));
     CK(e, cudaMemsetAsync(e->prof, 0, sizeof(unsigned long long) * 32 * e->n_sms, e->stream));
     CK(e, cudaMalloc(&e->evlog, sizeof(unsigned long long) * 2 * 4096));
@@ -424,19 +432,25 @@ int setup_mega(fl_engine* e) {
     p.off_bars = (int)off; off += al((size_t)n_slots * 16, 128);
     p.off_ring = (int)off; off += (size_t)n_slots * slot_bytes;
     e->mega_smem = off;
-    int rc = dispatch_mega(qt, gs, c.head_size, [&](auto kern) -> int {
+    p.n_seqs = 1;
+    p.xchg_stride = e->xchg_stride;
+    p.cache_stride = (unsigned long long)c.n_layers * c.n_kv_heads * c.max_seq_len * c.head_size;
+    auto prepare = [&](auto kern) -> int {
         cudaError_t s = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->mega_smem);
         if (s != cudaSuccess) return set_err(e, FL_ERR_CUDA, "cudaFuncSetAttribute(megakernel, %zu): %s", e->mega_smem, cudaGetErrorString(s));
         int nb = 0;
         s = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kMegaThreads, e->mega_smem);
         if (s != cudaSuccess || nb < 1) return set_err(e, FL_ERR_CUDA, "megakernel does not fit an SM (smem %zu)", e->mega_smem);
         return FL_OK;
-    });
+    };
+    int rc = dispatch_mega(qt, gs, c.head_size, false, prepare);
+    if (rc == FL_OK && c.max_seqs > 1) rc = dispatch_mega(qt, gs, c.head_size, true, prepare);
     if (rc == FL_ERR_UNSUPPORTED) return set_err(e, rc, "megakernel: unsupported quant/group/head combination");
     return rc;
 }
 
-int launch_mega(fl_engine* e, int slot, int n_steps) {
+// slots [slot, slot + n_seqs): n_seqs == 1 is the plain kernel; more walk every phase once per sequence in one launch
+int launch_mega(fl_engine* e, int slot, int n_steps, int n_seqs = 1) {
     const fl_config& c = e->c;
     MegaParams p = e->mega;
     const size_t cache_per_slot = (size_t)c.n_layers * c.n_kv_heads * c.max_seq_len * c.head_size;
@@ -446,9 +460,15 @@ int launch_mega(fl_engine* e, int slot, int n_steps) {
     p.out_tokens = e->out_tokens + (size_t)slot * e->out_cap;
     p.argmax_out = e->argmax_dev + slot;
     p.n_steps = n_steps;
+    p.n_seqs = n_seqs;
+    if (slot > 0) {     // the exchange buffers of slot 0 serve a single sequence in any slot; a batch starts at its own block
+        const size_t o = n_seqs > 1 ? (size_t)slot * e->xchg_stride : 0;
+        auto sh = [&](auto*& ptr) { ptr = reinterpret_cast<std::remove_reference_t<decltype(ptr)>>(reinterpret_cast<uint8_t*>(ptr) + o); };
+        sh(p.x1t); sh(p.qkvt); sh(p.attnt); sh(p.hdt); sh(p.score_t); sh(p.am);
+    }
     p.epoch = e->epoch;
     e->epoch += (uint32_t)n_steps * (uint32_t)(c.n_layers + 1) * kTagsPerLayer;
-    return dispatch_mega(c.quant_type, c.group_size, c.head_size, [&](auto kern) -> int {
+    return dispatch_mega(c.quant_type, c.group_size, c.head_size, n_seqs > 1, [&](auto kern) -> int {
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(e->n_sms); cfg.blockDim = dim3(kMegaThreads); cfg.dynamicSmemBytes = e->mega_smem; cfg.stream = e->stream;
         cudaLaunchAttribute attr[1];
@@ -634,7 +654,7 @@ void fl_destroy(fl_engine* e) {
     fr(e->x1); fr(e->qkv_buf); fr(e->attn); fr(e->hd); fr(e->logits); fr(e->tap_qkv); fr(e->tap_norm);
     fr(e->k_cache); fr(e->v_cache); fr(e->rope); fr(e->states); fr(e->out_tokens); fr(e->in_tokens); fr(e->argmax_dev);
     fr(e->ag_send); fr(e->ag_recv);
-    fr(e->mega_layers); fr(e->x1t); fr(e->qkvt); fr(e->attnt); fr(e->hdt); fr(e->score_t); fr(e->am); fr(e->prof); fr(e->evlog);
+    fr(e->mega_layers); fr(e->xchg); fr(e->prof); fr(e->evlog);
     if (e->h_tokens) cudaFreeHost(e->h_tokens);
     if (e->h_logits) cudaFreeHost(e->h_logits);
     if (e->h_argmax) cudaFreeHost(e->h_argmax);
@@ -798,11 +818,25 @@ int fl_forward_batch(fl_engine* e, int n_seqs, const int32_t* tokens, const int3
         e->h_tokens[i] = tokens[i];
     }
     CK(e, cudaMemcpyAsync(e->in_tokens, e->h_tokens, sizeof(int) * n_seqs, cudaMemcpyHostToDevice, e->stream));
-    for (int i = 0; i < n_seqs; ++i) {
-        set_state_kernel<<<1, 1, 0, e->stream>>>(e->states + i, e->in_tokens, i, pos[i], 1, 0);
-        e->launches += 1;
-        int rc = run_step(e, i);
-        if (rc) return rc;
+    if (e->use_mega && n_seqs > 1 && !getenv("FL_NO_MULTISEQ")) {
+        // one persistent launch per group of up to kMaxSeqsPerLaunch sequences: every phase is walked once per sequence, so the
+        // exchanges and serial sections of one sequence hide behind the weight streaming of the others
+        for (int i = 0; i < n_seqs; ++i) {
+            set_state_kernel<<<1, 1, 0, e->stream>>>(e->states + i, e->in_tokens, i, pos[i], 1, 0);
+            e->launches += 1;
+        }
+        for (int i = 0; i < n_seqs; i += kMaxSeqsPerLaunch) {
+            const int n = n_seqs - i < kMaxSeqsPerLaunch ? n_seqs - i : kMaxSeqsPerLaunch;
+            int rc = launch_mega(e, i, 1, n);
+            if (rc) return rc;
+        }
+    } else {
+        for (int i = 0; i < n_seqs; ++i) {
+            set_state_kernel<<<1, 1, 0, e->stream>>>(e->states + i, e->in_tokens, i, pos[i], 1, 0);
+            e->launches += 1;
+            int rc = run_step(e, i);
+            if (rc) return rc;
+        }
     }
     if (argmax_out) CK(e, cudaMemcpyAsync(e->h_argmax, e->argmax_dev, sizeof(int) * n_seqs, cudaMemcpyDeviceToHost, e->stream));
     CK(e, cudaStreamSynchronize(e->stream));

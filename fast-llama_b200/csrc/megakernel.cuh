@@ -100,7 +100,38 @@ struct MegaParams {
     // dynamic shared memory carve-up (byte offsets)
     int off_ring, off_xq, off_xs, off_xt, off_chain, off_att, off_misc, off_bars, off_vstage, off_vbars, off_pairs, off_psrc, off_geom;
     int v_chunk_rows, n_vchunks;     // V ring of the attention part: n_vchunks chunks of v_chunk_rows rows x HS/cph floats
+    // several sequences in one launch (fl_forward_batch): sequence s uses the exchange buffers at + s * xchg_stride bytes, the
+    // caches at + s * cache_stride floats, st[s], out_tokens + s * out_cap, argmax_out[s].  Every phase is walked once per
+    // sequence back to back, so one sequence's exchanges and serial sections hide behind the others' weight streaming, and
+    // the second pass over a phase's weights is served from L2.
+    int n_seqs;
+    unsigned long long xchg_stride, cache_stride;
 };
+
+constexpr int kMaxSeqsPerLaunch = 16;      // per-sequence state lives in 64 spare words of the misc block
+
+// the per-sequence buffers of a launch (MS = false: the single sequence the pointers in MegaParams already describe)
+struct SeqView {
+    uint2 *x1t, *qkvt, *attnt, *hdt, *score_t;
+    uint4* am;
+    float *kc, *vc;
+};
+template <bool MS>
+__device__ __forceinline__ SeqView seq_view(const MegaParams& p, int s) {
+    SeqView v{p.x1t, p.qkvt, p.attnt, p.hdt, p.score_t, p.am, p.k_cache, p.v_cache};
+    if (MS) {
+        const unsigned long long o = p.xchg_stride * (unsigned long long)s;
+        v.x1t = reinterpret_cast<uint2*>(reinterpret_cast<char*>(p.x1t) + o);
+        v.qkvt = reinterpret_cast<uint2*>(reinterpret_cast<char*>(p.qkvt) + o);
+        v.attnt = reinterpret_cast<uint2*>(reinterpret_cast<char*>(p.attnt) + o);
+        v.hdt = reinterpret_cast<uint2*>(reinterpret_cast<char*>(p.hdt) + o);
+        v.score_t = reinterpret_cast<uint2*>(reinterpret_cast<char*>(p.score_t) + o);
+        v.am = reinterpret_cast<uint4*>(reinterpret_cast<char*>(p.am) + o);
+        v.kc = p.k_cache + p.cache_stride * (unsigned long long)s;
+        v.vc = p.v_cache + p.cache_stride * (unsigned long long)s;
+    }
+    return v;
+}
 
 // ---------------------------------------------------------------------------------------------- PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -609,7 +640,7 @@ __device__ __forceinline__ float pv_rows(const float* vb, const float* wp, int D
 }
 
 template <int HS>
-__device__ __forceinline__ void attention_part(const MegaParams& p, uint8_t* smem, int layer, int qh, int part, int pos, int bs,
+__device__ __forceinline__ void attention_part(const MegaParams& p, const SeqView sv, uint8_t* smem, int layer, int qh, int part, int pos, int bs,
                                                uint32_t tag_qkv, uint32_t tag_score, uint32_t tag_out, uint32_t phases_drained, int tid, Prof& pf) {
     constexpr int EPL = HS / 8;
     const int cph = p.cph;
@@ -631,8 +662,8 @@ __device__ __forceinline__ void attention_part(const MegaParams& p, uint8_t* sme
     const int n = pos + 1;
     const int warp = tid >> 5, lane = tid & 31;
     const size_t cache_off = ((size_t)layer * p.n_kv_heads + kvh) * p.max_seq * HS;
-    float* kc = p.k_cache + cache_off;
-    float* vc = p.v_cache + cache_off + (size_t)part * p.max_seq * DW;      // this part's column block: [max_seq / 4][DW][4 positions]
+    float* kc = sv.kc + cache_off;
+    float* vc = sv.vc + cache_off + (size_t)part * p.max_seq * DW;      // this part's column block: [max_seq / 4][DW][4 positions]
     const int d0 = part * DW;
 
     // ---- V ring: chunk c = cached rows [c*VR, min(pos, (c+1)*VR)) of the column block, one bulk copy each
@@ -684,7 +715,7 @@ __device__ __forceinline__ void attention_part(const MegaParams& p, uint8_t* sme
         // sequence_rope_v2 (tensor.h:262-270) walks all bs*hgs rows of the q tensor with position pos0 + row: query head g
         // of a GQA group is rotated at pos + g*bs (== pos when n_heads == n_kv_heads).  Reproduced, not fixed.
         const float2 cs2 = __ldg(reinterpret_cast<const float2*>(p.rope) + (size_t)(sect == 0 ? pos + g * bs : pos) * (HS / 2) + i);
-        const uint2* src = p.qkvt + (sect == 0 ? (size_t)qh * HS : sect == 1 ? (size_t)dim + (size_t)kvh * HS : (size_t)dim + kv_dim + (size_t)kvh * HS) + 2 * i;
+        const uint2* src = sv.qkvt + (sect == 0 ? (size_t)qh * HS : sect == 1 ? (size_t)dim + (size_t)kvh * HS : (size_t)dim + kv_dim + (size_t)kvh * HS) + 2 * i;
         uint4 w = ld_tag2(src);
         while (w.y != tag_qkv || w.w != tag_qkv) w = ld_tag2(src);
         const float x0 = __uint_as_float(w.x), x1 = __uint_as_float(w.z);
@@ -704,7 +735,7 @@ __device__ __forceinline__ void attention_part(const MegaParams& p, uint8_t* sme
         } else {
             v_s[2 * i] = x0; v_s[2 * i + 1] = x1;
             if (g == 0 && part == 0) {
-                float* vblk = p.v_cache + cache_off + (size_t)((2 * i) / DW) * p.max_seq * DW + ((size_t)(pos >> 2) * DW + (2 * i) % DW) * 4 + (pos & 3);
+                float* vblk = sv.vc + cache_off + (size_t)((2 * i) / DW) * p.max_seq * DW + ((size_t)(pos >> 2) * DW + (2 * i) % DW) * 4 + (pos & 3);
                 vblk[0] = x0; vblk[4] = x1;
             }
         }
@@ -715,7 +746,7 @@ __device__ __forceinline__ void attention_part(const MegaParams& p, uint8_t* sme
     pf.mark(tid, 30, pf.trace_slot >= 0);
 
     // ---- scores for this part's keys: float dot_product_avx256 (x86_simd.cpp:1447-1468): 8 FMA chains, then 0 + l0 + ... + l7
-    uint2* att_g = p.score_t + (size_t)qh * p.score_stride;
+    uint2* att_g = sv.score_t + (size_t)qh * p.score_stride;
     {
         const float* qj = q_s + j;                 // q values of this AVX lane are re-read from shared memory (registers are scarce)
 #pragma unroll 1
@@ -841,7 +872,7 @@ __device__ __forceinline__ void attention_part(const MegaParams& p, uint8_t* sme
             if (n_chunks == 0) o = __fmul_rn(v, w);
             else if (fabsf(w) > 1e-15f) o = __fmaf_rn(v, w, o);
         }
-        st_tag(p.attnt + (size_t)qh * HS + d0 + pvt, o, tag_out);
+        st_tag(sv.attnt + (size_t)qh * HS + d0 + pvt, o, tag_out);
         (void)c_wait; (void)c_loop; (void)c_rest;
         if (pvt == 0) {
             *vcount = vbase + (uint32_t)n_chunks;
@@ -855,9 +886,10 @@ __device__ __forceinline__ void attention_part(const MegaParams& p, uint8_t* sme
 }
 
 // ---------------------------------------------------------------------------------------------- the kernel
-template <int QT, int GS, int HS>
+template <int QT, int GS, int HS, bool MS = false>
 __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __grid_constant__ MegaParams p) {
     using RK = Rk<QT, GS>;
+    const int n_seqs = MS ? p.n_seqs : 1;
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t* ring = smem + p.off_ring;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.off_bars);
@@ -903,6 +935,8 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
                 for (int pi = 0; pi < n_phases; ++pi) {
                     const int* pg = geom + ((pi == n_phases - 1) ? 4 : (pi & 3)) * kGeomStride;
                     const int n_stages = pg[PG_NKC] * pg[PG_TT];      // per tile
+#pragma unroll 1
+                    for (int sq = 0; sq < n_seqs; ++sq) {
                     const uint8_t* src = reinterpret_cast<const uint8_t* const*>(smem + p.off_psrc)[pi];      // the stream is laid out in issue order
 #pragma unroll 1
                     for (int t = 0; t < pg[PG_NT]; ++t) {
@@ -921,6 +955,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
                             src += bytes;
                             if (++slot == (uint32_t)n_slots) { slot = 0; par ^= 1u; }
                         }
+                    }
                     }
                 }
             }
@@ -949,7 +984,10 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
                 struct { int tt, M; } ph = {pg[PG_TT], pg[PG_M]};
                 pf.ev = ((step == p.n_steps - 1) && (layer == p.n_layers / 2) && pk < 4 && p.evlog && (p.debug_skip & 16) && (blockIdx.x == 7 || blockIdx.x == gridDim.x - 3)) ? p.evlog + (blockIdx.x == 7 ? 0 : 4096) : nullptr;
                 const uint32_t tl = tbase + (uint32_t)layer * kTagsPerLayer;
-                uint2* out = (pk == 0) ? p.qkvt : (pk == 2) ? p.hdt : p.x1t;
+#pragma unroll 1
+                for (int sq = 0; sq < n_seqs; ++sq) {
+                const SeqView sv = seq_view<MS>(p, sq);
+                uint2* out = (pk == 0) ? sv.qkvt : (pk == 2) ? sv.hdt : sv.x1t;
                 const uint32_t tag_out = tl + ((pk == 0) ? 1u : (pk == 1) ? 4u : (pk == 2) ? 5u : 6u);
                 struct { int rb, nt; } pt = {pg[PG_RB], pg[PG_NT]};
                 const int nkc = pg[PG_NKC], sk = pg[PG_SK], nsb = pg[PG_NSB];
@@ -963,7 +1001,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
                     const bool live = lane < R;
                     // residual input of this row (x1 += tmp, tensor.cpp:723): its word was validated by the consumers' earlier build
                     float x_old = 0.0f;
-                    if ((pk == 1 || pk == 3) && live) x_old = __ldcg(reinterpret_cast<const float*>(p.x1t + row));
+                    if ((pk == 1 || pk == 3) && live) x_old = __ldcg(reinterpret_cast<const float*>(sv.x1t + row));
                     float acc = 0.0f, acc2 = 0.0f;                     // acc2: the W3 row of the fused W1/W3 stream
 #pragma unroll 1
                     for (int j = 0; j < nsb; ++j) {
@@ -1000,7 +1038,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
                         else if (pk == 2) v = swiglu_exact(acc, acc2);
                         else v = __fadd_rn(x_old, acc);
                         if (pk == 4) {
-                            p.logits[row] = v;
+                            if (!MS) p.logits[row] = v;        // fl_forward_batch returns token ids only
                             if (v > best_v || (v == best_v && row < best_i)) { best_v = v; best_i = row; }
                         } else {
                             st_tag(out + row, v, tag_out);
@@ -1020,7 +1058,8 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
                         const int oi = __shfl_xor_sync(kFull, bi, o);
                         if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
                     }
-                    if (lane == 0) st_relaxed_v4(p.am + blockIdx.x, make_uint4(__float_as_uint(bv), tag_am, (uint32_t)bi, tag_am));
+                    if (lane == 0) st_relaxed_v4(sv.am + blockIdx.x, make_uint4(__float_as_uint(bv), tag_am, (uint32_t)bi, tag_am));
+                }
                 }
             }
         }
@@ -1048,20 +1087,24 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
 
     // sequence state at launch: written by the previous kernel on this stream.  Kept in shared memory, not registers:
     // the phase loop below is register-bound (168 per thread with 9 warps on 4 schedulers) and must not spill.
-    int* sstate = reinterpret_cast<int*>(misc) + 26;          // [0] next token, [1] n_out
-    if (tid == 0) { sstate[0] = p.st->token; sstate[1] = p.st->n_out; }
+    // several sequences: [4 * s + {0 token, 1 n_out, 2 pos at launch, 3 bs at launch}] in the free tail of the misc block
+    int* sstate = reinterpret_cast<int*>(misc) + (MS ? 448 : 26);          // [0] next token, [1] n_out
+    if (MS) {
+        if (tid < n_seqs) { sstate[4 * tid] = p.st[tid].token; sstate[4 * tid + 1] = p.st[tid].n_out; sstate[4 * tid + 2] = p.st[tid].pos; sstate[4 * tid + 3] = p.st[tid].bs; }
+    } else if (tid == 0) { sstate[0] = p.st->token; sstate[1] = p.st->n_out; }
     const int pos0 = p.st->pos, bs0 = p.st->bs;
     consumer_sync();
 
 #pragma unroll 1
     for (int step = 0; step < p.n_steps; ++step) {
         const uint32_t tbase = p.epoch + 1u + (uint32_t)step * (uint32_t)(p.n_layers + 1) * kTagsPerLayer;   // tag(layer, k) = tbase + layer * 8 + k
-        const int pos = pos0 + step, bs = step == 0 ? bs0 : 1;
         // embedding row (transformer.cpp:115-122): this CTA's slice of it becomes the input vector of layer 0
-        {
-            const int token = sstate[0];
+#pragma unroll 1
+        for (int sq = 0; sq < n_seqs; ++sq) {
+            const int token = sstate[MS ? 4 * sq : 0];
             const int e0 = (int)((long long)p.dim * blockIdx.x / gridDim.x), e1 = (int)((long long)p.dim * (blockIdx.x + 1) / gridDim.x);
-            for (int i = e0 + tid; i < e1; i += kConsumerThreads) st_tag(p.x1t + i, __ldg(p.emb + (size_t)token * p.dim + i), tbase);
+            uint2* x1t = seq_view<MS>(p, sq).x1t;
+            for (int i = e0 + tid; i < e1; i += kConsumerThreads) st_tag(x1t + i, __ldg(p.emb + (size_t)token * p.dim + i), tbase);
         }
         pf.stop(tid, 19);
 #pragma unroll 1
@@ -1070,8 +1113,12 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
             const uint32_t tl = tbase + (uint32_t)layer * kTagsPerLayer;
             // tags: +0 layer input (= +6 of the previous layer), +1 qkv, +2 scores, +3 attention out, +4 x1 after Wo, +5 hd, +6 x1 after W2
             const uint32_t tag_x_in = (layer == 0) ? tbase : tl - kTagsPerLayer + 6u;
+#pragma unroll 1
+            for (int sq = 0; sq < n_seqs; ++sq) {
+            const SeqView sv = seq_view<MS>(p, sq);
+            const int pos = (MS ? sstate[4 * sq + 2] : pos0) + step;
             // ---- the activation vector of this phase
-            const uint2* in = (pk == 1) ? p.attnt : (pk == 3) ? p.hdt : p.x1t;
+            const uint2* in = (pk == 1) ? sv.attnt : (pk == 3) ? sv.hdt : sv.x1t;
             const uint32_t tag_in = (pk == 1) ? tl + 3u : (pk == 2) ? tl + 4u : (pk == 3) ? tl + 5u : tag_x_in;
             const float* gain = (pk == 0) ? p.att_norm + (size_t)layer * p.dim : (pk == 2) ? p.ffn_norm + (size_t)layer * p.dim : (pk == 4) ? p.out_norm : nullptr;
             const bool traced = (step == p.n_steps - 1) && (layer == p.n_layers / 2) && pk < 4;
@@ -1087,8 +1134,6 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
             const int* pg = geom + pk * kGeomStride;
             struct { int tt, M; } ph = {pg[PG_TT], pg[PG_M]};
             // ---- drain this CTA's stages of the phase
-            uint2* out = (pk == 0) ? p.qkvt : (pk == 2) ? p.hdt : p.x1t;
-            const uint32_t tag_out = tl + ((pk == 0) ? 1u : (pk == 1) ? 4u : (pk == 2) ? 5u : 6u);
             {
                 struct { int nt; } pt = {pg[PG_NT]};
                 const int nkc = pg[PG_NKC], sk = pg[PG_SK], nsb = pg[PG_NSB];
@@ -1159,8 +1204,8 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
                 if (warp == 0) {
                     float bv = -INFINITY; int bi = 0x7fffffff;
                     for (int i = lane; i < (int)gridDim.x; i += 32) {
-                        uint4 w = ld_relaxed_v4(p.am + i);
-                        while (w.y != tag_am || w.w != tag_am) { __nanosleep(100); w = ld_relaxed_v4(p.am + i); }
+                        uint4 w = ld_relaxed_v4(sv.am + i);
+                        while (w.y != tag_am || w.w != tag_am) { __nanosleep(100); w = ld_relaxed_v4(sv.am + i); }
                         const float v = __uint_as_float(w.x); const int ix = (int)w.z;
                         if (v > bv || (v == bv && ix < bi)) { bv = v; bi = ix; }
                     }
@@ -1172,24 +1217,30 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
                     }
                     if (lane == 0) {
                         if (bi == 0x7fffffff) bi = 0;
-                        sstate[0] = bi;
+                        sstate[MS ? 4 * sq : 0] = bi;
                         if (blockIdx.x == 0) {
                             // sequence state for the host and the next launch
-                            SeqState* st = p.st;
-                            *p.argmax_out = bi;
-                            const int n_out = sstate[1];
-                            if (n_out < p.out_cap) p.out_tokens[n_out] = bi;
+                            SeqState* st = p.st + (MS ? sq : 0);
+                            p.argmax_out[MS ? sq : 0] = bi;
+                            const int n_out = sstate[MS ? 4 * sq + 1 : 1];
+                            if (n_out < p.out_cap) p.out_tokens[(MS ? (size_t)sq * p.out_cap : 0) + n_out] = bi;
                             st->n_out = n_out + 1; st->token = bi; st->pos = pos + 1; st->bs = 1;
-                            sstate[1] = n_out + 1;
+                            sstate[MS ? 4 * sq + 1 : 1] = n_out + 1;
                         }
                     }
                 }
                 consumer_sync();
             }
+            }       // sequences
             if (pk == 0 && attn_cta && !(p.debug_skip & 8)) {
-                // ---- attention (transformer.cpp:136, :397-455)
+                // ---- attention (transformer.cpp:136, :397-455), one sequence after the other
                 consumer_sync();            // the V stage aliases the activation image the other warps may still be draining with
-                attention_part<HS>(p, smem, layer, my_head, my_part, pos, bs, tl + 1u, tl + 2u, tl + 3u, phases_drained, tid, pf);
+#pragma unroll 1
+                for (int sq = 0; sq < n_seqs; ++sq) {
+                    const int pos = (MS ? sstate[4 * sq + 2] : pos0) + step;
+                    const int bs = step == 0 ? (MS ? sstate[4 * sq + 3] : bs0) : 1;
+                    attention_part<HS>(p, seq_view<MS>(p, sq), smem, layer, my_head, my_part, pos, bs, tl + 1u, tl + 2u, tl + 3u, phases_drained, tid, pf);
+                }
             }
         }
         pf.stop(tid, 18);

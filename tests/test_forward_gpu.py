@@ -138,6 +138,57 @@ def test_kv_slots_are_independent_and_batch_matches_single(fl):
     eng.close()
 
 
+BATCH_CASES = [("tiny-int8-5", TINY, Q_INT8, 64, 5), ("tiny64-int8-18", TINY64, Q_INT8, 64, 18), ("gqa-int8-3", GQA, Q_INT8, 64, 3),
+               ("tiny-int16-4", TINY, Q_INT16, 64, 4)]
+
+
+@pytest.mark.parametrize("name,spec,qt,gs,n_seqs", BATCH_CASES, ids=[c[0] for c in BATCH_CASES])
+def test_forward_batch_one_launch_for_all_sequences_matches_oracle(fl, name, spec, qt, gs, n_seqs):
+    """fl_forward_batch walks every phase once per sequence inside ONE persistent launch (groups of 16): sequences at
+    different positions, each compared token by token with the oracle's own greedy run of that sequence."""
+    w = gen_weights(spec, seed=6)
+    qm = quantize_model(spec, w, qt, gs)
+    pm = make_port_model(spec, qm, qt, gs)
+    P = port()
+    n_steps = 8
+    prompts = [prompt_tokens(spec, 2 + (3 * i) % 7, seed=20 + i) for i in range(n_seqs)]
+    want = []
+    logits = np.empty(spec.vocab_size, np.float32)
+    for pr in prompts:
+        P.port_model_reset(pm)
+        P.port_forward(pm, ptr(pr), pr.size, 0, ptr(logits))
+        seq = [P.port_argmax(ptr(logits), spec.vocab_size)]
+        for k in range(n_steps):
+            t = np.array([seq[-1]], np.int32)
+            P.port_forward(pm, ptr(t), 1, pr.size + k, ptr(logits))
+            seq.append(P.port_argmax(ptr(logits), spec.vocab_size))
+        want.append(seq)
+    eng = make_engine(fl, spec, qm, qt, gs, max_seqs=n_seqs)
+    toks = np.array([eng.forward(pr, 0, slot=i, want_logits=False, want_argmax=True) for i, pr in enumerate(prompts)], np.int32)
+    pos = np.array([pr.size for pr in prompts], np.int32)
+    got = [[int(t)] for t in toks]
+    before = eng.launch_count()
+    for _ in range(n_steps):
+        toks = eng.forward_batch(toks, pos)
+        pos += 1
+        for i, t in enumerate(toks):
+            got[i].append(int(t))
+    launches = eng.launch_count() - before
+    assert launches == n_steps * (n_seqs + (n_seqs + 15) // 16), launches      # one state update per sequence + one launch per 16
+    for i in range(n_seqs):
+        assert got[i] == want[i], (name, i)
+    # a single-sequence call on a used slot still continues that sequence correctly
+    nxt = eng.forward(np.array([got[1][-1]], np.int32), int(pos[1]), slot=1, want_logits=False, want_argmax=True)
+    P.port_model_reset(pm)
+    pr = prompts[1]
+    P.port_forward(pm, ptr(pr), pr.size, 0, ptr(logits))
+    for k, tk in enumerate(want[1]):
+        P.port_forward(pm, ptr(np.array([tk], np.int32)), 1, pr.size + k, ptr(logits))
+    assert nxt == P.port_argmax(ptr(logits), spec.vocab_size)
+    P.port_model_free(pm)
+    eng.close()
+
+
 LONG_CASES = [
     # name, spec, quant, group, new tokens: long enough that the persistent kernel refills its V-chunk ring (context beyond the
     # chunks that fit shared memory), takes a second batch of K rows (> 96 keys per CTA of a head) and crosses chunk boundaries
