@@ -274,17 +274,24 @@ def _parse_tokenizer(buf, off):
                 special={k: special[i] for k, i in (("bos", 1), ("eos", 2), ("pad", 3)) if special[i] >= 0})
 
 
-def engine_from_flm(path, max_seq_len=1024, device=0, **engine_kw):
-    """Load an .flm the way `main -c model.flm` does and return (finalized Engine, cfg, vocab).  The reference caps the
+def engine_from_flm(path, quant_type=Q_INT8, max_seq_len=1024, device=0, **engine_kw):
+    """Load an .flm the way `main -c model.flm [-q int8]` does and return (finalized Engine, cfg, vocab).  An int8 / int16
+    file is uploaded as stored; an f32 file (quant_type 0 in its config) has its matrices quantised at load with
+    `quant_type` and the file's group size, exactly what the reference's worker initialisation does
+    (transformer.cpp:289-304: tgt.quantize(src)); the embedding table and the norms stay fp32.  The reference caps the
     context at 1024 whatever the file says (transformer.cpp:32); pass max_seq_len to lift that."""
+    from .loaders import quantize_rows
     cfg, t, vocab = read_flm(path)
-    qt = cfg["quant_type"]
+    qt = cfg["quant_type"] or quant_type
     if qt not in (Q_INT8, Q_INT16):
-        raise FlmError(f"{path}: quant_type {qt}: only int8 / int16 files run on the device (an f32 .flm is quantised at "
-                       "load by the reference; use loaders.quantize_rows on its tensors first)")
+        raise FlmError(f"{path}: quant_type {qt} is not supported (int8 / int16)")
+    gs = cfg["quant_group_size"]
     eng = Engine(cfg["dim"], cfg["hidden_dim"], cfg["n_layers"], cfg["n_heads"], cfg["n_kv_heads"], cfg["vocab_size"],
-                 max_seq_len=max_seq_len, quant_type=qt, group_size=cfg["quant_group_size"], device=device, **engine_kw)
+                 max_seq_len=max_seq_len, quant_type=qt, group_size=gs, device=device, **engine_kw)
     for (kind, layer), (q, s) in t.items():
-        eng.upload(kind, layer, np.ascontiguousarray(q), None if s is None else np.ascontiguousarray(s))
+        q = np.ascontiguousarray(q)
+        if s is None and q.ndim == 2 and kind != T_TOK_EMB:
+            q, s = quantize_rows(q, qt, gs)
+        eng.upload(kind, layer, q, None if s is None else np.ascontiguousarray(s))
     eng.finalize()
     return eng, cfg, vocab

@@ -184,3 +184,48 @@ def test_engine_from_flm_matches_reference_golden_logits(fl, tmp_path):
         assert np.array_equal(bits(got), bits(g["decode_logits"][i])), i
         pos += 1
     eng.close()
+
+
+def f32_tensors(fl, spec, w):
+    return {(fl.flm.TENSOR_TYPES[tt][0], layer): (np.ascontiguousarray(arr, np.float32), None) for _, tt, layer, arr in fi.hf_tensors(spec, w)}
+
+
+def test_f32_file_quantised_at_load_equals_the_int8_file(fl, tmp_path):
+    """an f32 .flm (quant_type 0) whose matrices are quantised at load gives the tensors the int8 .flm stores (SURVEY 8c);
+    live: the reference loading the f32 file with -q int8 produces the golden logits of the int8 file"""
+    spec = TINY
+    w = gen_weights(spec, seed=1)
+    p32 = tmp_path / "tiny_f32.flm"
+    fl.flm.write_flm(p32, fi.config_of(spec, 0, 64, "tiny"), f32_tensors(fl, spec, w), fi.micro_vocab(spec.vocab_size))
+    cfg, t, _ = fl.flm.read_flm(p32)
+    assert cfg["quant_type"] == 0
+    want = fi.quantized_tensors(fl, spec, w, Q_INT8, 64)
+    for key, (q, s) in t.items():
+        assert s is None and q.dtype == np.float32
+        if q.ndim == 2 and key[0] != fl.T_TOK_EMB:
+            gq, gs_ = fl.loaders.quantize_rows(np.ascontiguousarray(q), Q_INT8, 64)
+            assert np.array_equal(gq, want[key][0]) and np.array_equal(bits(gs_), bits(want[key][1])), key
+    R = ref()
+    if R is not None:
+        g = np.load(FLM_GOLDEN)
+        h = R.ref_model_load(str(p32).encode(), b"", 1, Q_INT8, 2, 64, 0)
+        assert h
+        prompt = g["prompt"].astype(np.int32)
+        a = np.empty(spec.vocab_size, np.float32)
+        R.ref_forward(h, ptr(prompt), prompt.size, 0, ptr(a))
+        assert np.array_equal(bits(a), bits(g["prefill_logits"]))
+        R.ref_model_free(h)
+
+
+@pytest.mark.gpu
+def test_engine_from_f32_flm_matches_reference_golden_logits(fl, tmp_path):
+    spec = TINY
+    w = gen_weights(spec, seed=1)
+    p32 = tmp_path / "tiny_f32.flm"
+    fl.flm.write_flm(p32, fi.config_of(spec, 0, 64, "tiny"), f32_tensors(fl, spec, w), fi.micro_vocab(spec.vocab_size))
+    g = np.load(FLM_GOLDEN)
+    eng, cfg, _ = fl.flm.engine_from_flm(p32, quant_type=Q_INT8)
+    prompt = g["prompt"].astype(np.int32)
+    got = eng.forward(prompt, 0)
+    assert np.array_equal(bits(got), bits(g["prefill_logits"]))
+    eng.close()
