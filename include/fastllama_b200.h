@@ -100,7 +100,10 @@ int  fl_finalize(fl_engine* e);
 int  fl_forward(fl_engine* e, int seq_slot, const int32_t* tokens, int n_tokens, int pos,
                 float* logits_out, int32_t* argmax_out);
 
-/* One decode step for n_seqs independent sequences (slots 0..n_seqs-1): tokens[i] at pos[i] -> argmax_out[i]. */
+/* One decode step for n_seqs independent sequences (slots 0..n_seqs-1): tokens[i] at pos[i] -> argmax_out[i].
+ * (new; the reference has one KV cache and one position)  Up to 16 sequences share ONE persistent launch:
+ * every phase is walked once per sequence, each with its own cache slot and position; per-sequence results are
+ * bit-identical to fl_forward on that sequence alone.  Logits are not kept in this mode (token ids only). */
 int  fl_forward_batch(fl_engine* e, int n_seqs, const int32_t* tokens, const int32_t* pos, int32_t* argmax_out);
 
 /* Greedy generation with the token fed back on the device (no host round trip per token):
