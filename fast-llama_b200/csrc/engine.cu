@@ -349,7 +349,7 @@ int dispatch_mega(int qt, int gs, int hs, bool multi, F&& f) {
 // one-time set-up of the persistent decode kernel: layer table, counters, shared-memory carve-up
 int setup_mega(fl_engine* e) {
     const fl_config& c = e->c;
-    const int L = c.n_layers, qt = c.quant_type, gs = c.group_size, es = es_of(qt), gpl = 64 / gs;
+    const int L = c.n_layers, qt = c.quant_type, gs = c.group_size, es = es_of(qt);
     std::vector<MegaLayer> tab(L);
     for (int l = 0; l < L; ++l) {
         tab[l].qkv = e->rk_qkv[l].d; tab[l].wo = e->rk_wo[l].d; tab[l].w13 = e->rk_w13[l].d; tab[l].w2 = e->rk_w2[l].d;
