@@ -432,7 +432,7 @@ __device__ __forceinline__ float sumsq_chain_t(const float* xt, int n, int lane)
 // registers while warp 0 walks the sum-of-squares chain (max |(x*w)*r| == (max |x*w|)*r: rounding is monotonic, r > 0).
 template <int QT, int GS>
 __device__ __forceinline__ void build_activation(uint8_t* xq, float* xs, float* xt, float* misc, const uint2* src, uint32_t tag,
-                                                 const float* gain, int K, float* tap, int tid, Prof& pf) {
+                                                 const float* gain, int K, float* tap, int tid, Prof& pf, uint32_t* gate = nullptr, uint32_t gate_val = 0u) {
     using RK = Rk<QT, GS>;
     constexpr int PER = GS / 8;                 // values per thread per group
     constexpr int LPP = PER / 2;                // 16-byte loads per thread per pass
@@ -486,6 +486,7 @@ __device__ __forceinline__ void build_activation(uint8_t* xq, float* xs, float* 
         if (b0 == 0) {
             // every warp has left the previous phase (its drain / attention read the image this build overwrites)
             consumer_sync();
+            if (gate && tid == 0) st_shared_volatile_u32(gate, gate_val);       // the input is here: the producer may prefetch again
             // zero the padded tail so padded groups contribute fma(0, 0, acc) == acc
             for (int i = K * RK::ES + tid * 4; i < kpad_bytes; i += kConsumerThreads * 4) *reinterpret_cast<uint32_t*>(xq + i) = 0u;
             for (int i = G + tid; i < (kpad_bytes / kStageRowBytes) * RK::GPS; i += kConsumerThreads) xs[i] = 0.0f;
@@ -641,7 +642,8 @@ __device__ __forceinline__ float pv_rows(const float* vb, const float* wp, int D
 
 template <int HS>
 __device__ __forceinline__ void attention_part(const MegaParams& p, const SeqView sv, uint8_t* smem, int layer, int qh, int part, int pos, int bs,
-                                               uint32_t tag_qkv, uint32_t tag_score, uint32_t tag_out, uint32_t phases_drained, int tid, Prof& pf) {
+                                               uint32_t tag_qkv, uint32_t tag_score, uint32_t tag_out, uint32_t phases_drained, int tid, Prof& pf,
+                                               uint32_t* gate = nullptr, uint32_t gate_val = 0u) {
     constexpr int EPL = HS / 8;
     const int cph = p.cph;
     const int DW = HS / cph;                                // head dims owned by this part
@@ -741,6 +743,7 @@ __device__ __forceinline__ void attention_part(const MegaParams& p, const SeqVie
         }
     }
     consumer_sync();
+    if (gate && tid == 0) st_shared_volatile_u32(gate, gate_val);               // q / k / v are here: Wo's prefetch may start
     pf.stop(tid, 10);
     pf.log(lane, warp, 16, 0);
     pf.mark(tid, 30, pf.trace_slot >= 0);
@@ -908,6 +911,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
         reinterpret_cast<uint32_t*>(smem + p.off_misc)[25] = 0u;
         reinterpret_cast<uint32_t*>(smem + p.off_misc)[31] = 0u;
         reinterpret_cast<uint32_t*>(smem + p.off_misc)[29] = 0u;      // phases the chain warp has finished
+        reinterpret_cast<uint32_t*>(smem + p.off_misc)[20] = 0u;      // prefetch gate: phases (counted over all steps) the producer may stream
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     const int n_phases = 4 * p.n_layers + 1;
@@ -935,6 +939,15 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
                 for (int pi = 0; pi < n_phases; ++pi) {
                     const int* pg = geom + ((pi == n_phases - 1) ? 4 : (pi & 3)) * kGeomStride;
                     const int n_stages = pg[PG_NKC] * pg[PG_TT];      // per tile
+                    // Prefetch gate.  Between two drains every CTA polls the tagged words of its next input, and those loads
+                    // queue behind whatever the 148 producers have in flight (Little's law: 148 x 175 KB = 4 us at HBM speed).
+                    // The ring refill for the NEXT phase is not needed before that input has arrived, so it is held back
+                    // until the consumers say so (after their poll), and then runs during the rebuild's arithmetic.
+                    if (!MS && !(p.debug_skip & (8 | 32))) {
+                        const uint32_t need = (uint32_t)(step * n_phases + pi) + 1u;
+                        const uint32_t* gate = reinterpret_cast<const uint32_t*>(smem + p.off_misc) + 20;
+                        while ((int)(ld_shared_volatile_u32(gate) - need) < 0) __nanosleep(64);
+                    }
 #pragma unroll 1
                     for (int sq = 0; sq < n_seqs; ++sq) {
                     const uint8_t* src = reinterpret_cast<const uint8_t* const*>(smem + p.off_psrc)[pi];      // the stream is laid out in issue order
@@ -1127,7 +1140,14 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
             pf.log(lane, warp, 8, pk);          // build starts
             {
                 const int K = (pk == 3) ? p.hidden : p.dim;
-                if (!(p.debug_skip & 8)) build_activation<QT, GS>(xq, xs, xt, misc, in, tag_in, gain, K, (pk == 4 && blockIdx.x == 0) ? p.tap_norm : nullptr, tid, pf);
+                // gate value after this poll (for the two-batch hd poll: after its first batch): this phase may be streamed; Wo is
+                // released by the attention part once q / k / v are in (or at once where this CTA has no attention to do)
+                uint32_t* gate = MS ? nullptr : reinterpret_cast<uint32_t*>(smem + p.off_misc) + 20;
+                const uint32_t gpi = (uint32_t)(step * n_phases + pi);
+                const bool no_attn_here = !(attn_cta && !(p.debug_skip & 8));
+                const uint32_t gate_val = gpi + ((pk == 0 && no_attn_here) ? 2u : 1u);
+                if (!(p.debug_skip & 8)) build_activation<QT, GS>(xq, xs, xt, misc, in, tag_in, gain, K, (pk == 4 && blockIdx.x == 0) ? p.tap_norm : nullptr, tid, pf,
+                                                                  (pk == 1) ? nullptr : gate, gate_val);
             }
             pf.stop(tid, 1);
             pf.log(lane, warp, 7, pk);          // drain starts
@@ -1239,7 +1259,8 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
                 for (int sq = 0; sq < n_seqs; ++sq) {
                     const int pos = (MS ? sstate[4 * sq + 2] : pos0) + step;
                     const int bs = step == 0 ? (MS ? sstate[4 * sq + 3] : bs0) : 1;
-                    attention_part<HS>(p, seq_view<MS>(p, sq), smem, layer, my_head, my_part, pos, bs, tl + 1u, tl + 2u, tl + 3u, phases_drained, tid, pf);
+                    attention_part<HS>(p, seq_view<MS>(p, sq), smem, layer, my_head, my_part, pos, bs, tl + 1u, tl + 2u, tl + 3u, phases_drained, tid, pf,
+                                       MS ? nullptr : reinterpret_cast<uint32_t*>(smem + p.off_misc) + 20, (uint32_t)(step * n_phases + pi) + 2u);
                 }
             }
         }
