@@ -486,7 +486,9 @@ __device__ __forceinline__ void build_activation(uint8_t* xq, float* xs, float* 
         if (b0 == 0) {
             // every warp has left the previous phase (its drain / attention read the image this build overwrites)
             consumer_sync();
-            if (gate && tid == 0) st_shared_volatile_u32(gate, gate_val);       // the input is here: the producer may prefetch again
+            // the input is here: the producer may prefetch again (measured: releasing later - after the chain, or after the
+            // second batch of the hd poll - costs more ring prefetch than it saves in contention)
+            if (gate && tid == 0) st_shared_volatile_u32(gate, gate_val);
             // zero the padded tail so padded groups contribute fma(0, 0, acc) == acc
             for (int i = K * RK::ES + tid * 4; i < kpad_bytes; i += kConsumerThreads * 4) *reinterpret_cast<uint32_t*>(xq + i) = 0u;
             for (int i = G + tid; i < (kpad_bytes / kStageRowBytes) * RK::GPS; i += kConsumerThreads) xs[i] = 0.0f;
@@ -743,7 +745,6 @@ __device__ __forceinline__ void attention_part(const MegaParams& p, const SeqVie
         }
     }
     consumer_sync();
-    if (gate && tid == 0) st_shared_volatile_u32(gate, gate_val);               // q / k / v are here: Wo's prefetch may start
     pf.stop(tid, 10);
     pf.log(lane, warp, 16, 0);
     pf.mark(tid, 30, pf.trace_slot >= 0);
@@ -797,6 +798,7 @@ __device__ __forceinline__ void attention_part(const MegaParams& p, const SeqVie
         }
     }
     consumer_sync();
+    if (gate && tid == 0) st_shared_volatile_u32(gate, gate_val);       // q / k / v and the scores are in: Wo's prefetch may start (softmax and PV give it time)
     pf.stop(tid, 12);
     pf.log(lane, warp, 13, 0);
 
