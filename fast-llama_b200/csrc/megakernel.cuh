@@ -952,6 +952,12 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
                     }
 #pragma unroll 1
                     for (int sq = 0; sq < n_seqs; ++sq) {
+                    if (MS && !(p.debug_skip & (8 | 32))) {
+                        // several sequences: every (phase, sequence) pass is released by that sequence's own poll
+                        const uint32_t need = (uint32_t)((step * n_phases + pi) * n_seqs + sq) + 1u;
+                        const uint32_t* gate = reinterpret_cast<const uint32_t*>(smem + p.off_misc) + 20;
+                        while ((int)(ld_shared_volatile_u32(gate) - need) < 0) __nanosleep(64);
+                    }
                     const uint8_t* src = reinterpret_cast<const uint8_t* const*>(smem + p.off_psrc)[pi];      // the stream is laid out in issue order
 #pragma unroll 1
                     for (int t = 0; t < pg[PG_NT]; ++t) {
@@ -1144,12 +1150,12 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
                 const int K = (pk == 3) ? p.hidden : p.dim;
                 // gate value after this poll (for the two-batch hd poll: after its first batch): this phase may be streamed; Wo is
                 // released by the attention part once q / k / v are in (or at once where this CTA has no attention to do)
-                uint32_t* gate = MS ? nullptr : reinterpret_cast<uint32_t*>(smem + p.off_misc) + 20;
-                const uint32_t gpi = (uint32_t)(step * n_phases + pi);
+                uint32_t* gate = reinterpret_cast<uint32_t*>(smem + p.off_misc) + 20;
+                const uint32_t gpi = MS ? (uint32_t)((step * n_phases + pi) * n_seqs + sq) : (uint32_t)(step * n_phases + pi);
                 const bool no_attn_here = !(attn_cta && !(p.debug_skip & 8));
-                const uint32_t gate_val = gpi + ((pk == 0 && no_attn_here) ? 2u : 1u);
+                const uint32_t gate_val = gpi + ((!MS && pk == 0 && no_attn_here) ? 2u : 1u);
                 if (!(p.debug_skip & 8)) build_activation<QT, GS>(xq, xs, xt, misc, in, tag_in, gain, K, (pk == 4 && blockIdx.x == 0) ? p.tap_norm : nullptr, tid, pf,
-                                                                  (pk == 1) ? nullptr : gate, gate_val);
+                                                                  (!MS && pk == 1) ? nullptr : gate, gate_val);
             }
             pf.stop(tid, 1);
             pf.log(lane, warp, 7, pk);          // drain starts
