@@ -14,5 +14,6 @@ from .binding import (Engine, Sampler, FlConfig, FlError, lib, lib_path, Q_INT8,
                       FLAG_NO_GRAPH, FLAG_NO_PDL, FLAG_NO_MEGAKERNEL, FLAG_PROFILE, ops, EXPORTED_SYMBOLS)
 
 from . import shard, loaders, flm, gguf_file, tokenizer
+from .generate import generate_text
 
-__all__ = ["shard", "loaders", "flm", "gguf_file", "tokenizer", "Engine", "Sampler", "FlConfig", "FlError", "lib", "lib_path", "ops", "EXPORTED_SYMBOLS"]
+__all__ = ["shard", "loaders", "flm", "gguf_file", "tokenizer", "generate_text", "Engine", "Sampler", "FlConfig", "FlError", "lib", "lib_path", "ops", "EXPORTED_SYMBOLS"]

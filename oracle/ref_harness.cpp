@@ -243,6 +243,31 @@ int ref_generate(void* h, const int* prompt, int n_prompt, int max_new, float te
     return n;
 }
 
+/* generate(prompt text) through the reference's public API (transformer.cpp:54-75): encode, generate, decode piece by piece.
+ * Writes the sampled token ids to out_tokens and the concatenated pieces to out_text; returns the number of tokens. */
+int ref_generate_text(void* h, const char* prompt, int max_new, float temperature, float topp, uint64_t seed,
+                      int* out_tokens, int tok_cap, char* out_text, int text_cap) {
+    auto& pt = static_cast<RefModel*>(h)->pt;
+    pt._sampler._rng_state = seed;
+    std::string text;
+    int n = 0;
+    int prev = -1;
+    /* the text callback does not hand out token ids; run the token-level generate with the same decode rule (:66-71) */
+    auto ids = pt.encode(prompt);
+    if (ids.empty()) return 0;
+    pt.generate(ids, [&](std::span<const int> toks, int, bool) -> bool {
+        if (n < tok_cap) out_tokens[n] = toks[0];
+        ++n;
+        text += pt._tkn.decode(toks[0], prev);
+        prev = toks[0];
+        return n < tok_cap;
+    }, max_new, temperature, topp);
+    int len = int(text.size()) < text_cap - 1 ? int(text.size()) : text_cap - 1;
+    memcpy(out_text, text.data(), size_t(len));
+    out_text[len] = 0;
+    return n;
+}
+
 int ref_encode(void* h, const char* text, int* out, int cap) {
     auto v = static_cast<RefModel*>(h)->pt.encode(text);
     int n = int(v.size()) < cap ? int(v.size()) : cap;
