@@ -122,7 +122,7 @@ def _config_bytes(cfg):
 def _tokenizer_bytes(vocab):
     """vocab = dict(vocab_type (1 bpe / 2 spm), texts [str], scores [float], types [int], special {name: id})"""
     def enc(t):
-        b = t.encode("utf-8") + b"\0"
+        b = t.encode("utf-8", "surrogateescape") + b"\0"
         return b + b"\0" * _pad(len(b), 8)
     toks, text = [], b""
     for t, score, typ in zip(vocab["texts"], vocab["scores"], vocab["types"]):
@@ -268,7 +268,7 @@ def _parse_tokenizer(buf, off):
     text = bytes(buf[tb:tb + text_size])
 
     def s(p):
-        return text[p:text.index(b"\0", p)].decode("utf-8")
+        return text[p:text.index(b"\0", p)].decode("utf-8", "surrogateescape")      # pieces need not be valid UTF-8
     return dict(vocab_type=vocab_type, texts=[s(int(p)) for p in items["index"]], show=[s(int(p)) for p in items["show"]],
                 scores=items["score"].tolist(), types=items["type"].tolist(), conn_tag=s(conn_pos),
                 special={k: special[i] for k, i in (("bos", 1), ("eos", 2), ("pad", 3)) if special[i] >= 0})

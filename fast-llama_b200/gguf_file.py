@@ -71,7 +71,7 @@ class _Cursor:
             raise GgufError("string runs past the end of the file")
         s = bytes(self.buf[self.pos:self.pos + n])
         self.pos += n
-        return s.decode("utf-8", "replace")
+        return s.decode("utf-8", "surrogateescape")      # vocabulary pieces need not be valid UTF-8: keep their bytes
 
     def value(self, vtype):
         if vtype == V_STRING:

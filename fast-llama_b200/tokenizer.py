@@ -22,9 +22,10 @@ _PRINTABLE_OR_SPACE = set(range(0x20, 0x7F)) | {0x09, 0x0A, 0x0B, 0x0C, 0x0D}
 class Tokenizer:
     def __init__(self, texts, scores, show=None, conn_tag=CONN_TAG, bos=1, eos=2, pad=0):
         """texts: the pieces (bytes or str) indexed by token id; show: their display form (default: the same)"""
-        tb = [t.encode("utf-8") if isinstance(t, str) else bytes(t) for t in texts]
+        enc = lambda t: t.encode("utf-8", "surrogateescape") if isinstance(t, str) else bytes(t)      # noqa: E731
+        tb = [enc(t) for t in texts]
         self.texts = tb
-        self.show = tb if show is None else [t.encode("utf-8") if isinstance(t, str) else bytes(t) for t in show]
+        self.show = tb if show is None else [enc(t) for t in show]
         self.scores = np.asarray(scores, np.float32)
         self.bos, self.eos, self.pad = bos, eos, pad
         self.text2id = {t: i for i, t in enumerate(tb)}                # a repeated piece keeps its LAST id (:153-155)
@@ -43,7 +44,7 @@ class Tokenizer:
     def from_gguf_vocab(cls, vocab):
         """vocab dict returned by gguf_file.read_gguf (set_token_texts, tokenizer.cpp:74-120): connector pieces are displayed
         with a leading space; special ids default to 1 / 2 / 0"""
-        texts = [t.encode("utf-8") for t in vocab["texts"]]
+        texts = [t.encode("utf-8", "surrogateescape") for t in vocab["texts"]]
         show = [b" " + t[len(CONN_TAG):] if t.startswith(CONN_TAG) else t for t in texts]
         sp = vocab.get("special", {})
         return cls(texts, vocab["scores"], show, CONN_TAG, sp.get("bos", 1), sp.get("eos", 2), sp.get("pad", 0))
