@@ -109,7 +109,7 @@ class Tokenizer:
 
         def push(i):
             j = nxt[i]
-            if j < 0:
+            if j < 0 or sym[i] >= len(self.texts) or sym[j] >= len(self.texts):      # byte fallback ids beyond a tiny vocabulary
                 return
             tid = self._search(self.texts[sym[i]] + self.texts[sym[j]])
             if tid != -1 and self.scores[tid] > np.float32(-1e10):

@@ -233,12 +233,13 @@ def test_engine_from_f32_flm_matches_reference_golden_logits(fl, tmp_path):
 
 def test_vocabulary_pieces_keep_their_raw_bytes(fl, tmp_path):
     """a piece that is not valid UTF-8 (raw byte pieces exist in real vocabularies) survives write -> read -> tokenizer"""
-    spec = fi.MICRO
-    vocab = fi.micro_vocab(spec.vocab_size)
+    import tokenizer_inputs as ti
+    vocab = ti.merge_vocab()
+    spec = ti.spec_for(vocab)
     raw = b"\xff\xfeab"
-    vocab["texts"][10] = raw.decode("utf-8", "surrogateescape")
+    vocab["texts"][300] = raw.decode("utf-8", "surrogateescape")
     p = tmp_path / "m.flm"
     fl.flm.write_flm(p, fi.config_of(spec, Q_INT8, 64, "x"), fi.quantized_tensors(fl, spec, gen_weights(spec, seed=2), Q_INT8, 64), vocab)
     T = fl.tokenizer.Tokenizer.from_flm_vocab(fl.flm.read_flm(p, tensors=False)[2])
-    assert T.texts[10] == raw and T.decode([10]) == raw
-    assert T.encode(raw, add_bos=False) != []            # bytes in, ids out (falls back to byte tokens where no piece matches)
+    assert T.texts[300] == raw and T.decode([300]) == raw
+    assert T.encode(b"\xff", add_bos=False) == [0xff + 3]            # an unknown byte falls back to its byte token
