@@ -286,7 +286,7 @@ def run_ours(args, rank, world, local_rank):
                 "scope": f"decode_megakernel, {'ONE persistent launch' if world == 1 else 'one launch per token (+ token all-gather),'} = {n_dec} tokens (every phase of every layer of every token); algorithmic "
                          f"bytes per token = INT8 weights + fp32 group scales + fp32 KV read/write at mean ctx {mean_ctx:.0f} = {step_bytes / 1e9:.3f} GB "
                          "(SURVEY 8d); achieved = bytes per token / measured time per token (CUDA events on the engine stream)",
-                "traffic": 7.379e9, "traffic_note": "dram read 7.348 GB + write 0.032 GB per token from ncu --set full of a 1-token launch at ctx 288 (profiles/r01/ncu_full_megakernel_v4.csv)",
+                "traffic": 7.383e9, "traffic_note": "dram read 7.353 GB + write 0.030 GB per token from ncu --set full of a 1-token launch at ctx 288 (profiles/r01/ncu_full_megakernel_v6.csv)",
                 "peak_source": peak_src, "frac_of_8TBs": achieved / 8000.0}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
