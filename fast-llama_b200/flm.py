@@ -110,12 +110,14 @@ def _config_bytes(cfg):
     out = _Out()
     for k in CONFIG_FIELDS:
         v = cfg.get(k, CONFIG_DEFAULTS[k])
-        if isinstance(CONFIG_DEFAULTS[k], str):
-            _block(out, k, str(v).encode("utf-8") + b"\0", B_STRING, D_INT8)      # BlockDataType.CHAR == 1
-        elif isinstance(CONFIG_DEFAULTS[k], float):
-            out.put(_item(k, "f", D_FLOAT32, float(v)))
-        else:
-            out.put(_item(k, "i", D_INT32, int(v)))
+        # the converter picks the item type from the VALUE (ModelConfig.serialize_as_flf, :386-398): a config.json whose
+        # hidden_act is "silu" leaves a string in act_type, and that is what ends up in the file
+        if type(v) is str:
+            _block(out, k, v.encode("utf-8") + b"\0", B_STRING, D_INT8)      # BlockDataType.CHAR == 1
+        elif type(v) is float:
+            out.put(_item(k, "f", D_FLOAT32, v))
+        elif type(v) is int:
+            out.put(_item(k, "i", D_INT32, v))
     return out.bytes()
 
 
