@@ -217,6 +217,16 @@ def _read_block_header(buf, pos):
 
 
 def read_flm(path, tensors=True):
+    """see _read_flm; any parsing failure on a malformed file surfaces as FlmError (the reference's loader returns false)"""
+    try:
+        return _read_flm(path, tensors)
+    except FlmError:
+        raise
+    except (ValueError, IndexError, OverflowError, KeyError, struct.error, MemoryError) as e:
+        raise FlmError(f"{path}: malformed .flm file ({type(e).__name__}: {e})") from e
+
+
+def _read_flm(path, tensors=True):
     """-> (cfg dict, {(engine kind, layer): (payload, scales | None)}, vocab dict | None).  Arrays are views into one
     memory map of the file (no copy until upload)."""
     buf = np.memmap(path, np.uint8, "r")

@@ -104,6 +104,16 @@ def split_q8_0(raw, rows, cols):
 
 
 def read_gguf(path, strict=True, tensors=True):
+    """see _read_gguf; any parsing failure on a malformed file surfaces as GgufError (the reference's loader returns false)"""
+    try:
+        return _read_gguf(path, strict, tensors)
+    except GgufError:
+        raise
+    except (ValueError, IndexError, OverflowError, KeyError, struct.error, MemoryError) as e:
+        raise GgufError(f"{path}: malformed GGUF file ({type(e).__name__}: {e})") from e
+
+
+def _read_gguf(path, strict=True, tensors=True):
     """-> (cfg dict, {(engine kind, layer): (payload, scales | None)}, vocab dict)"""
     buf = np.memmap(path, np.uint8, "r")
     c = _Cursor(buf)
