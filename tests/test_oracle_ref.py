@@ -108,6 +108,45 @@ def test_forward_vs_reference_forward(spec):
     R.ref_model_free(h)
 
 
+def test_reference_chunked_prefill_equals_token_by_token_oracle():
+    """The engine feeds a prompt token by token; the reference runs it as bs > 1 forwards of at most max_batch_size
+    tokens (its scratch buffers are sized for that).  A 100-token prompt through the REAL reference in chunks of
+    48 + 52 must leave the same logits (and the same cache: decode continues identically) as the oracle fed one token at a time.
+    (Chunks stay well below the harness's max_batch_size of 64: at 63-64 tokens per forward the reference overruns its own
+    scratch buffers - glibc reports "corrupted size vs. prev_size" - and every later result is garbage; DESIGN.md defect D11.)"""
+    P, R = port(), ref()
+    spec = TINY
+    w = gen_weights(spec, seed=23)
+    with tempfile.TemporaryDirectory() as d:
+        write_llama2c(d + "/m.bin", spec, w)
+        write_tokenizer_bin(d + "/t.bin", synthetic_vocab(spec.vocab_size))
+        h = R.ref_model_load((d + "/m.bin").encode(), (d + "/t.bin").encode(), 3, Q_INT8, 2, 64, 0)
+    assert h
+    qm = quantize_model(spec, w, Q_INT8, 64)
+    pc = PortConfig(spec.dim, spec.hidden_dim, spec.n_layers, spec.n_heads, spec.n_kv_heads, spec.head_size, spec.vocab_size, 1024, Q_INT8, 64)
+    pm = P.port_model_create(C.byref(pc))
+    for (k, l), (q, s) in qm.items():
+        P.port_model_set_tensor(pm, k, l, ptr(q), ptr(s) if s is not None else None, q.shape[0] if q.ndim == 2 else 1, q.shape[-1])
+    toks = prompt_tokens(spec, 100, seed=4)
+    a, b = np.empty(spec.vocab_size, np.float32), np.empty(spec.vocab_size, np.float32)
+    for i in range(toks.size):                                   # oracle: one token per forward, like the engine
+        P.port_forward(pm, ptr(toks[i:i + 1].copy()), 1, i, ptr(a))
+    pos = 0
+    for n in (48, 52):                                           # reference: two batched forwards
+        chunk = toks[pos:pos + n].copy()
+        R.ref_forward(h, ptr(chunk), n, pos, ptr(b))
+        pos += n
+    assert beq(a, b)
+    for _ in range(6):
+        t = np.array([int(np.argmax(b))], np.int32)
+        P.port_forward(pm, ptr(t), 1, pos, ptr(a))
+        R.ref_forward(h, ptr(t), 1, pos, ptr(b))
+        assert beq(a, b), pos
+        pos += 1
+    P.port_model_free(pm)
+    R.ref_model_free(h)
+
+
 @pytest.mark.skipif(ref_native() is None, reason="libref_native.so not built (host without avx512f)")
 def test_native_avx512_build_is_bit_identical_to_haswell_build():
     R, N = ref(), ref_native()
