@@ -140,14 +140,17 @@ def test_oracle_on_our_reader_matches_reference_golden_logits(fl, tmp_path):
     P.port_model_free(pm)
 
 
-def test_reference_loader_accepts_our_file_live(fl, tmp_path):
+@pytest.mark.parametrize("qt", [Q_INT8, Q_INT16], ids=["int8", "int16"])
+def test_reference_loader_accepts_our_file_live(fl, tmp_path, qt):
+    """also the only way to pin INT16 end to end on the real reference: its llama2.c path always stores int8 weights and then
+    throws in matmul when asked for -q int16 (tensor.cpp:556-561); an int16 .flm carries int16 weights"""
     R = ref()
     if R is None:
         pytest.skip("oracle/_ref not built (GPU box): covered by tests/golden/flm_golden.npz")
     # multi-head only: the reference's own grouped-query path leaves all but the first query head of a group unset
     # (Tensor::weighted_sum passes out.rows() instead of total_rows(), tensor.cpp:713; DESIGN.md defect D10)
     from fixtures import TINY64
-    spec, qt, gs = TINY64, Q_INT8, 64
+    spec, gs = TINY64, 64
     w = gen_weights(spec, seed=8)
     p = tmp_path / "tiny64.flm"
     fl.flm.write_flm(p, fi.config_of(spec, qt, gs, "tiny64"), fi.quantized_tensors(fl, spec, w, qt, gs),
@@ -164,6 +167,13 @@ def test_reference_loader_accepts_our_file_live(fl, tmp_path):
     R.ref_forward(h, ptr(prompt), prompt.size, 0, ptr(a))
     P.port_forward(pm, ptr(prompt), prompt.size, 0, ptr(b))
     assert np.array_equal(bits(a), bits(b))
+    pos = prompt.size
+    for _ in range(6):                                           # and decode
+        t = np.array([int(np.argmax(a))], np.int32)
+        R.ref_forward(h, ptr(t), 1, pos, ptr(a))
+        P.port_forward(pm, ptr(t), 1, pos, ptr(b))
+        assert np.array_equal(bits(a), bits(b)), pos
+        pos += 1
     R.ref_model_free(h)
     P.port_model_free(pm)
 
