@@ -140,17 +140,19 @@ def test_oracle_on_our_reader_matches_reference_golden_logits(fl, tmp_path):
     P.port_model_free(pm)
 
 
-@pytest.mark.parametrize("qt", [Q_INT8, Q_INT16], ids=["int8", "int16"])
-def test_reference_loader_accepts_our_file_live(fl, tmp_path, qt):
+@pytest.mark.parametrize("qt,gs", [(Q_INT8, 64), (Q_INT16, 64), (Q_INT8, 32)], ids=["int8", "int16", "int8-g32"])
+def test_reference_loader_accepts_our_file_live(fl, tmp_path, qt, gs):
     """also the only way to pin INT16 end to end on the real reference: its llama2.c path always stores int8 weights and then
-    throws in matmul when asked for -q int16 (tensor.cpp:556-561); an int16 .flm carries int16 weights"""
+    throws in matmul when asked for -q int16 (tensor.cpp:556-561); an int16 .flm carries int16 weights.  Likewise 32-wide
+    groups (config 5's Q8_0 arithmetic): the reference's GGUF path mis-decodes the scales (D5), an .flm with
+    quant_group_size 32 goes through correctly"""
     R = ref()
     if R is None:
         pytest.skip("oracle/_ref not built (GPU box): covered by tests/golden/flm_golden.npz")
     # multi-head only: the reference's own grouped-query path leaves all but the first query head of a group unset
     # (Tensor::weighted_sum passes out.rows() instead of total_rows(), tensor.cpp:713; DESIGN.md defect D10)
     from fixtures import TINY64
-    spec, gs = TINY64, 64
+    spec = TINY64
     w = gen_weights(spec, seed=8)
     p = tmp_path / "tiny64.flm"
     fl.flm.write_flm(p, fi.config_of(spec, qt, gs, "tiny64"), fi.quantized_tensors(fl, spec, w, qt, gs),
