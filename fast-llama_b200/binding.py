@@ -8,7 +8,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 Q_INT16, Q_INT8 = 1, 2
 (T_TOK_EMB, T_ATT_NORM, T_WQ, T_WK, T_WV, T_WO, T_FFN_NORM, T_W1, T_W2, T_W3, T_OUT_NORM, T_CLS) = range(12)
-FLAG_NO_GRAPH, FLAG_NO_PDL, FLAG_NO_MEGAKERNEL, FLAG_PROFILE = 1, 2, 4, 8
+FLAG_NO_GRAPH, FLAG_NO_PDL, FLAG_NO_MEGAKERNEL, FLAG_PROFILE, FLAG_NO_TC = 1, 2, 4, 8, 16
 
 EXPORTED_SYMBOLS = [
     "fl_create", "fl_destroy", "fl_last_error", "fl_upload", "fl_finalize", "fl_forward", "fl_forward_batch",
@@ -16,6 +16,7 @@ EXPORTED_SYMBOLS = [
     "fl_decode_async", "fl_stream", "fl_device_ptr", "fl_profile_read", "fl_sync", "fl_launch_count", "fl_step_bytes", "fl_tap",
     "fl_set_comm", "fl_allgather_tokens", "fl_op_quantize", "fl_op_matmul_q", "fl_op_rmsnorm", "fl_op_rope",
     "fl_op_softmax", "fl_op_swiglu", "fl_op_expf", "fl_op_attn_decode", "fl_op_argmax",
+    "fl_decode_batch_async", "fl_op_matmul_q_tc", "fl_read_out_tokens",
 ]
 
 
@@ -59,6 +60,9 @@ def lib():
     L.fl_forward_batch.argtypes = [vp, C.c_int, vp, vp, vp]
     L.fl_generate_greedy.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, vp, i32p]
     L.fl_decode_async.argtypes = [vp, C.c_int, C.c_int]
+    L.fl_decode_batch_async.argtypes = [vp, C.c_int, C.c_int]
+    L.fl_read_out_tokens.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.fl_op_matmul_q_tc.argtypes = [C.c_int, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, C.c_int, vp, C.c_int]
     L.fl_stream.argtypes = [vp]
     L.fl_stream.restype = vp
     L.fl_device_ptr.argtypes = [vp, C.c_char_p, C.c_int]
@@ -122,6 +126,17 @@ class _Ops:
         out = np.empty((x.shape[0], m), np.float32)
         _check(lib().fl_op_matmul_q(qt, gs, _p(np.ascontiguousarray(w)), _p(np.ascontiguousarray(ws, np.float32)), m, n,
                                     _p(x), _p(np.ascontiguousarray(xs, np.float32)), x.shape[0], _p(out)))
+        return out
+
+    def matmul_q_tc(self, w, ws, x, xs, gs=64, w3=None, ws3=None, variant=0):
+        """quant::matmul for up to 64 activation rows in one weight pass on the tensor cores; with w3: swiglu(W x, W3 x)."""
+        m, n = w.shape
+        x = np.ascontiguousarray(x).reshape(-1, n)
+        out = np.empty((x.shape[0], m), np.float32)
+        w3c = None if w3 is None else np.ascontiguousarray(w3)
+        ws3c = None if ws3 is None else np.ascontiguousarray(ws3, np.float32)
+        _check(lib().fl_op_matmul_q_tc(gs, _p(np.ascontiguousarray(w)), _p(np.ascontiguousarray(ws, np.float32)), _p(w3c), _p(ws3c),
+                                       m, n, _p(x), _p(np.ascontiguousarray(xs, np.float32)), x.shape[0], _p(out), variant))
         return out
 
     def rmsnorm(self, x, w):
@@ -243,6 +258,16 @@ class Engine:
 
     def decode_async(self, n_steps, slot=0):
         _check(lib().fl_decode_async(self.h, slot, n_steps), self.h)
+
+    def decode_batch_async(self, n_seqs, n_steps):
+        """n_steps greedy steps of sequences 0..n_seqs-1 from their device-resident states: one weight pass per step."""
+        _check(lib().fl_decode_batch_async(self.h, n_seqs, n_steps), self.h)
+
+    def out_tokens(self, n, slot=0):
+        """the first n tokens sampled for `slot` since its last prefill"""
+        buf = np.zeros(n, np.int32)
+        _check(lib().fl_read_out_tokens(self.h, slot, n, _p(buf)), self.h)
+        return buf
 
     def sync(self):
         _check(lib().fl_sync(self.h), self.h)

@@ -7,6 +7,8 @@
 #include "../../include/fastllama_b200.h"
 #include "kernels.cuh"
 #include "megakernel.cuh"
+#include "tc_gemm.cuh"
+#include "batch_kernels.cuh"
 
 #include <dlfcn.h>
 #include <math.h>
@@ -15,6 +17,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <map>
 #include <string>
 #include <type_traits>
 #include <vector>
@@ -49,6 +52,7 @@ struct RkMat {
     size_t bytes = 0;
 };
 enum { RK_QKV = 0, RK_WO, RK_W13, RK_W2, RK_CLS, RK__COUNT };
+constexpr int kMaxRows = 64;          // activation rows per pass of the tensor-core path (MMA N)
 
 }  // namespace
 
@@ -104,6 +108,21 @@ struct fl_engine {
     bool finalized = false;
     int64_t launches = 0;
     int kernels_per_step = 0;
+    // tensor-core path (tc_gemm.cuh + batch_kernels.cuh): several activation rows per weight pass (prompt chunks, several sequences)
+    bool tc = false;
+    std::vector<RkMat> tc_qkv, tc_wo, tc_w13, tc_w2;   // stage-stream layout of tc_gemm.cuh
+    RkMat tc_cls;
+    unsigned long long* tc_off[RK__COUNT] = {};
+    size_t tc_bytes[RK__COUNT] = {};
+    float *bx1 = nullptr, *bqkv = nullptr, *batt = nullptr, *bhd = nullptr, *blogits = nullptr;   // [kMaxRows][...]
+    uint8_t *img_x = nullptr, *img_h = nullptr, *img_c = nullptr;       // activation images: dim-wide, hidden-wide, classifier input
+    RowMeta* rows = nullptr;            // device
+    RowMeta* h_rows = nullptr;          // pinned
+    int tc_smem = 0;
+    bool tap_rows = false;              // the last forward went through the rows path: taps come from its last row
+    int tap_row = 0;
+    std::map<int, cudaGraphExec_t> batch_graphs;     // device-resident decode step of n sequences (fl_decode_batch_async)
+    std::vector<int> h_pos;             // host mirror of every slot's next position (bounds checks)
     // NCCL (dlopen'ed; only when a communicator is bound)
     void* nccl_lib = nullptr;
     void* nccl_comm = nullptr;
@@ -508,6 +527,154 @@ int run_step(fl_engine* e, int slot) {
     return FL_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// tensor-core path: several activation rows per weight pass
+// ------------------------------------------------------------------------------------------------------------------
+int build_tc_table(fl_engine* e, int kind, int M, int K, int tt) {
+    const int G = e->n_sms, gs = e->c.group_size;
+    const int nkc = ceil_div(K, kTcKC);
+    std::vector<unsigned long long> off(G + 1, 0);
+    for (int c = 0; c < G; ++c) {
+        const TcPart pt = tc_part(M, c, G);
+        unsigned long long bytes = 0;
+        for (int t = 0; t < pt.nt; ++t) { int lr0, R; tc_tile(pt, t, lr0, R); bytes += (unsigned long long)nkc * tc_stage_a_bytes(R, tt, gs); }
+        off[c + 1] = off[c] + bytes;
+    }
+    e->tc_bytes[kind] = off[G];
+    CK(e, cudaMalloc(&e->tc_off[kind], sizeof(unsigned long long) * (G + 1)));
+    CK(e, cudaMemcpyAsync(e->tc_off[kind], off.data(), sizeof(unsigned long long) * (G + 1), cudaMemcpyHostToDevice, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    return FL_OK;
+}
+
+int alloc_tc(fl_engine* e, RkMat& m, int kind) {
+    m.bytes = e->tc_bytes[kind];
+    CK(e, cudaMalloc(&m.d, m.bytes + 4096));       // tail: an M = 128 MMA of a short last tile never reads past the allocation's stage
+    CK(e, cudaMemsetAsync(m.d, 0, m.bytes + 4096, e->stream));
+    return FL_OK;
+}
+
+// every kernel of the rows path is launched with programmatic stream serialisation (unless FL_FLAG_NO_PDL): it may start
+// while its predecessor drains; each kernel executes griddepcontrol.wait before it touches dependent data
+template <typename... KArgs, typename... Args>
+int launch_pdl(fl_engine* e, bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    cudaError_t s = cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+    if (s != cudaSuccess) return set_err(e, FL_ERR_CUDA, "kernel launch: %s", cudaGetErrorString(s));
+    if (e) e->launches += 1;
+    return FL_OK;
+}
+
+template <int GS, int N>
+int launch_qgemm_n(fl_engine* e, bool pdl, int epi, const TcGemmArgs& a, int grid, cudaStream_t st) {
+    auto go = [&](auto kern) -> int {
+        cudaError_t s = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, a.smem_bytes);
+        if (s != cudaSuccess) return set_err(e, FL_ERR_CUDA, "cudaFuncSetAttribute(qgemm, %d): %s", a.smem_bytes, cudaGetErrorString(s));
+        return launch_pdl(e, pdl, kern, dim3(grid), dim3(kTcThreads), (size_t)a.smem_bytes, st, a);
+    };
+    if (epi == TC_EPI_STORE) return go(qgemm_kernel<GS, N, false, TC_EPI_STORE>);
+    if (epi == TC_EPI_RESADD) return go(qgemm_kernel<GS, N, false, TC_EPI_RESADD>);
+    return go(qgemm_kernel<GS, N, true, TC_EPI_SWIGLU>);
+}
+
+// N = activation rows padded to 8 / 16 / 32 / 64
+int launch_qgemm(fl_engine* e, bool pdl, int gs, int N, int epi, const TcGemmArgs& a, int grid, cudaStream_t st) {
+#define FL_QG(GS_, N_) if (gs == GS_ && N == N_) return launch_qgemm_n<GS_, N_>(e, pdl, epi, a, grid, st);
+    FL_QG(64, 8) FL_QG(64, 16) FL_QG(64, 32) FL_QG(64, 64)
+    FL_QG(32, 8) FL_QG(32, 16) FL_QG(32, 32) FL_QG(32, 64)
+#undef FL_QG
+    return set_err(e, FL_ERR_UNSUPPORTED, "qgemm: group %d / N %d not supported", gs, N);
+}
+
+// One forward over T activation rows described by e->rows (device): every layer is one weight pass for all rows.
+//   n_cls == 0: no classifier;  n_cls == 1: only the last row (prompt chunk: transformer.cpp:140-142);  n_cls == T: every row.
+//   advance: the classified rows' sequence states move on (token fed back on the device); reset_out: their n_out restarts.
+int enqueue_rows(fl_engine* e, int T, int n_cls, int advance, int reset_out, cudaStream_t st) {
+    const fl_config& c = e->c;
+    const int gs = c.group_size, dim = c.dim, hid = c.hidden_dim, hs = c.head_size;
+    const int kv_dim = hs * c.n_kv_heads, qkv_rows = dim + 2 * kv_dim;
+    const int N = tc_pad_n(T);
+    const bool pdl = !(c.flags & FL_FLAG_NO_PDL);
+    const int G = e->n_sms;
+    int rc = launch_pdl(e, pdl, embed_rows_kernel, dim3(T), dim3(256), 0, st, (const float*)e->emb, (const RowMeta*)e->rows, e->bx1, dim);
+    if (rc) return rc;
+    const size_t cache_per_layer = (size_t)c.n_kv_heads * c.max_seq_len * hs;
+    const size_t cache_per_slot = cache_per_layer * c.n_layers;
+    auto rms_quant = [&](const float* x, size_t stride, const float* gain, uint8_t* img, int rows, int Nimg, float* tap) -> int {
+        if (gs == 64) return launch_pdl(e, pdl, rms_quant_rows_kernel<64>, dim3(rows), dim3(kThreads), (size_t)dim * 4, st, x, stride, gain, dim, img, Nimg, tap);
+        return launch_pdl(e, pdl, rms_quant_rows_kernel<32>, dim3(rows), dim3(kThreads), (size_t)dim * 4, st, x, stride, gain, dim, img, Nimg, tap);
+    };
+    auto quant = [&](const float* x, int K, uint8_t* img) -> int {
+        const dim3 grid(T, ceil_div(K / gs, kThreads / 8));
+        if (gs == 64) return launch_pdl(e, pdl, quant_rows_kernel<64>, grid, dim3(kThreads), 0, st, x, K, img, N);
+        return launch_pdl(e, pdl, quant_rows_kernel<32>, grid, dim3(kThreads), 0, st, x, K, img, N);
+    };
+    auto gemm = [&](const RkMat& w, int kind, const uint8_t* img, float* out, int M, int K, int rowsT, int Nimg, int ldo, int epi) -> int {
+        TcGemmArgs a{};
+        a.w = w.d; a.cta_off = e->tc_off[kind]; a.xq = img; a.out = out; a.M = M; a.K = K; a.T = rowsT; a.ldo = ldo;
+        a.smem_bytes = e->tc_smem; a.variant = 0;
+        return launch_qgemm(e, pdl, gs, Nimg, epi, a, G, st);
+    };
+    for (int l = 0; l < c.n_layers; ++l) {
+        const bool last = l == c.n_layers - 1;
+        // x2 = rmsnorm(x1); qkv = Wqkv * quantize(x2)                         (transformer.cpp:132-135)
+        rc = rms_quant(e->bx1, (size_t)dim, e->att_norm + (size_t)l * dim, e->img_x, T, N, nullptr);
+        if (!rc) rc = gemm(e->tc_qkv[l], RK_QKV, e->img_x, e->bqkv, qkv_rows, dim, T, N, qkv_rows, TC_EPI_STORE);
+        if (rc) return rc;
+        // RoPE, KV append, QK^T, softmax, PV                                  (:136, :397-455)
+        AttnRowsArgs a{};
+        a.qkv = e->bqkv;
+        a.k_cache = e->k_cache + (size_t)l * cache_per_layer;
+        a.v_cache = e->v_cache + (size_t)l * cache_per_layer;
+        a.slot_stride = cache_per_slot;
+        a.rope = e->rope; a.rows = e->rows; a.out = e->batt;
+        a.n_heads = c.n_heads; a.n_kv_heads = c.n_kv_heads;
+        a.attn_scale = 1.0f / sqrtf((float)hs);
+        a.vl.max_seq = c.max_seq_len;
+        a.vl.dw = e->want_mega ? hs / e->cph : hs;
+        a.vl.blocked4 = e->want_mega ? 1 : 0;
+        a.tap_qkv = last ? e->tap_qkv : nullptr;
+        a.tap_row = T - 1;
+        const size_t asmem = (size_t)(hs + 64 + c.max_seq_len + 8) * 4;
+        if (hs == 128) {
+            rc = launch_pdl(e, pdl, kv_append_rows_kernel<128>, dim3(c.n_kv_heads, T), dim3(128), 0, st, a);
+            if (!rc) rc = launch_pdl(e, pdl, attn_rows_kernel<128>, dim3(c.n_heads, T), dim3(kThreads), asmem, st, a);
+        } else {
+            rc = launch_pdl(e, pdl, kv_append_rows_kernel<64>, dim3(c.n_kv_heads, T), dim3(64), 0, st, a);
+            if (!rc) rc = launch_pdl(e, pdl, attn_rows_kernel<64>, dim3(c.n_heads, T), dim3(kThreads), asmem, st, a);
+        }
+        if (rc) return rc;
+        // x1 += Wo * quantize(attn)                                           (:138-139)
+        rc = quant(e->batt, dim, e->img_x);
+        if (!rc) rc = gemm(e->tc_wo[l], RK_WO, e->img_x, e->bx1, dim, dim, T, N, dim, TC_EPI_RESADD);
+        // hd = swiglu(W1 q, W3 q), q = quantize(rmsnorm(x1))                  (:144-147)
+        if (!rc) rc = rms_quant(e->bx1, (size_t)dim, e->ffn_norm + (size_t)l * dim, e->img_x, T, N, nullptr);
+        if (!rc) rc = gemm(e->tc_w13[l], RK_W13, e->img_x, e->bhd, hid, dim, T, N, hid, TC_EPI_SWIGLU);
+        // x1 += W2 * quantize(hd)                                             (:149-150)
+        if (!rc) rc = quant(e->bhd, hid, e->img_h);
+        if (!rc) rc = gemm(e->tc_w2[l], RK_W2, e->img_h, e->bx1, dim, hid, T, N, dim, TC_EPI_RESADD);
+        if (rc) return rc;
+    }
+    if (n_cls > 0) {
+        // logits = Wcls * quantize(rmsnorm(x1))                               (:154-160)
+        const int row0 = T - n_cls, Nc = tc_pad_n(n_cls);
+        rc = rms_quant(e->bx1 + (size_t)row0 * dim, (size_t)dim, e->out_norm, e->img_c, n_cls, Nc, e->tap_norm);
+        if (!rc) rc = gemm(e->tc_cls, RK_CLS, e->img_c, e->blogits, c.vocab_size, dim, n_cls, Nc, c.vocab_size, TC_EPI_STORE);
+        if (!rc) rc = launch_pdl(e, pdl, argmax_rows_kernel, dim3(n_cls), dim3(1024), 0, st, (const float*)e->blogits, c.vocab_size, c.vocab_size,
+                                 (const RowMeta*)e->rows, row0, e->states, e->out_tokens, e->out_cap, e->argmax_dev, advance, reset_out);
+        if (rc) return rc;
+    }
+    e->tap_rows = true;
+    e->tap_row = T - 1;
+    return FL_OK;
+}
+
 }  // namespace
 
 namespace {
@@ -545,6 +712,8 @@ int fl_create(const fl_config* cfg, int device, fl_engine** out) {
         return set_err(nullptr, FL_ERR_UNSUPPORTED, "fl_create: quant_type/group_size combination not supported");
     if (c.dim % 64 || c.hidden_dim % 64)
         return set_err(nullptr, FL_ERR_INVALID, "fl_create: dim and hidden_dim must be multiples of 64");
+    if (c.max_seq_len % 4)
+        return set_err(nullptr, FL_ERR_INVALID, "fl_create: max_seq_len must be a multiple of 4 (the V cache keeps 4 positions per block)");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
         return set_err(nullptr, FL_ERR_CUDA, "fl_create: no CUDA device (this library has no CPU path)");
@@ -597,9 +766,42 @@ int fl_create(const fl_config* cfg, int device, fl_engine** out) {
         }
         { int rc = alloc_packed(e, e->cls, c.vocab_size, c.vocab_size, c.dim); if (rc) return fail(rc); }
     }
+    e->tc = c.quant_type == FL_Q_INT8 && !(c.flags & FL_FLAG_NO_TC) && prop.major >= 10;
+    if (e->tc) {
+        e->tc_qkv.resize(L); e->tc_wo.resize(L); e->tc_w13.resize(L); e->tc_w2.resize(L);
+        int rc = build_tc_table(e, RK_QKV, c.dim + 2 * kv_dim, c.dim, 1);
+        if (!rc) rc = build_tc_table(e, RK_WO, c.dim, c.dim, 1);
+        if (!rc) rc = build_tc_table(e, RK_W13, c.hidden_dim, c.dim, 2);
+        if (!rc) rc = build_tc_table(e, RK_W2, c.dim, c.hidden_dim, 1);
+        if (!rc) rc = build_tc_table(e, RK_CLS, c.vocab_size, c.dim, 1);
+        for (int l = 0; l < L && !rc; ++l) {
+            rc = alloc_tc(e, e->tc_qkv[l], RK_QKV);
+            if (!rc) rc = alloc_tc(e, e->tc_wo[l], RK_WO);
+            if (!rc) rc = alloc_tc(e, e->tc_w13[l], RK_W13);
+            if (!rc) rc = alloc_tc(e, e->tc_w2[l], RK_W2);
+        }
+        if (!rc) rc = alloc_tc(e, e->tc_cls, RK_CLS);
+        if (rc) return fail(rc);
+        const int qkv_rows = c.dim + 2 * kv_dim;
+        CKF(cudaMalloc(&e->bx1, (size_t)kMaxRows * c.dim * 4));
+        CKF(cudaMalloc(&e->bqkv, (size_t)kMaxRows * qkv_rows * 4));
+        CKF(cudaMalloc(&e->batt, (size_t)kMaxRows * c.dim * 4));
+        CKF(cudaMalloc(&e->bhd, (size_t)kMaxRows * c.hidden_dim * 4));
+        CKF(cudaMalloc(&e->blogits, (size_t)kMaxRows * c.vocab_size * 4));
+        const size_t ix = tc_image_bytes(c.dim, kMaxRows, c.group_size), ih = tc_image_bytes(c.hidden_dim, kMaxRows, c.group_size);
+        CKF(cudaMalloc(&e->img_x, ix)); CKF(cudaMalloc(&e->img_h, ih)); CKF(cudaMalloc(&e->img_c, ix));
+        CKF(cudaMemsetAsync(e->img_x, 0, ix, e->stream)); CKF(cudaMemsetAsync(e->img_h, 0, ih, e->stream)); CKF(cudaMemsetAsync(e->img_c, 0, ix, e->stream));
+        CKF(cudaMalloc(&e->rows, sizeof(RowMeta) * kMaxRows));
+        CKF(cudaMallocHost(&e->h_rows, sizeof(RowMeta) * kMaxRows));
+        int max_smem = 0;
+        CKF(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+        e->tc_smem = max_smem - 28 * 1024;     // room for one small CTA of the neighbouring kernels next to a GEMM CTA
+    }
+    e->h_pos.assign(c.max_seqs, 0);
     const int es = es_of(c.quant_type);
     size_t max_elems = (size_t)c.vocab_size * c.dim;
     if ((size_t)c.hidden_dim * c.dim > max_elems) max_elems = (size_t)c.hidden_dim * c.dim;
+    if ((size_t)c.dim * c.dim > max_elems) max_elems = (size_t)c.dim * c.dim;
     e->staging_bytes = ((max_elems * es + 255) & ~(size_t)255) + max_elems / c.group_size * 4 + 256;
     CKF(cudaMalloc(&e->staging, e->staging_bytes));
 
@@ -620,6 +822,7 @@ int fl_create(const fl_config* cfg, int device, fl_engine** out) {
     e->out_cap = c.max_seq_len + 8;
     CKF(cudaMalloc(&e->out_tokens, sizeof(int) * (size_t)e->out_cap * c.max_seqs));
     e->in_cap = c.max_seq_len > 64 ? c.max_seq_len : 64;
+    if (c.max_seqs > e->in_cap) e->in_cap = c.max_seqs;
     CKF(cudaMalloc(&e->in_tokens, sizeof(int) * e->in_cap));
     CKF(cudaMalloc(&e->argmax_dev, sizeof(int) * c.max_seqs));
     CKF(cudaMalloc(&e->ag_send, sizeof(int) * 1024));
@@ -655,6 +858,15 @@ void fl_destroy(fl_engine* e) {
     fr(e->k_cache); fr(e->v_cache); fr(e->rope); fr(e->states); fr(e->out_tokens); fr(e->in_tokens); fr(e->argmax_dev);
     fr(e->ag_send); fr(e->ag_recv);
     fr(e->mega_layers); fr(e->xchg); fr(e->prof); fr(e->evlog);
+    for (auto& m : e->tc_qkv) fr(m.d);
+    for (auto& m : e->tc_wo) fr(m.d);
+    for (auto& m : e->tc_w13) fr(m.d);
+    for (auto& m : e->tc_w2) fr(m.d);
+    fr(e->tc_cls.d);
+    for (int k = 0; k < RK__COUNT; ++k) fr(e->tc_off[k]);
+    fr(e->bx1); fr(e->bqkv); fr(e->batt); fr(e->bhd); fr(e->blogits); fr(e->img_x); fr(e->img_h); fr(e->img_c); fr(e->rows);
+    if (e->h_rows) cudaFreeHost(e->h_rows);
+    for (auto& kv : e->batch_graphs) if (kv.second) cudaGraphExecDestroy(kv.second);
     if (e->h_tokens) cudaFreeHost(e->h_tokens);
     if (e->h_logits) cudaFreeHost(e->h_logits);
     if (e->h_argmax) cudaFreeHost(e->h_argmax);
@@ -703,6 +915,22 @@ int fl_upload(fl_engine* e, int kind, int layer, const void* q, const float* sca
             // dequantised once here; the reference dequantises the row per token (transformer.cpp:117-118), same bits
             dequant_rows_kernel<<<1024, 256, 0, e->stream>>>(e->staging, d_scales, e->emb, n, gs, qt);
         } else {
+            if (e->tc) {
+                RkMat* m = nullptr;
+                int kindk = 0, m_total = rows, row_base = 0, tt = 1, sub = 0;
+                switch (kind) {
+                    case FL_T_WQ: m = &e->tc_qkv[layer]; kindk = RK_QKV; m_total = c.dim + 2 * kv_dim; break;
+                    case FL_T_WK: m = &e->tc_qkv[layer]; kindk = RK_QKV; m_total = c.dim + 2 * kv_dim; row_base = c.dim; break;
+                    case FL_T_WV: m = &e->tc_qkv[layer]; kindk = RK_QKV; m_total = c.dim + 2 * kv_dim; row_base = c.dim + kv_dim; break;
+                    case FL_T_WO: m = &e->tc_wo[layer]; kindk = RK_WO; break;
+                    case FL_T_W1: m = &e->tc_w13[layer]; kindk = RK_W13; tt = 2; break;
+                    case FL_T_W3: m = &e->tc_w13[layer]; kindk = RK_W13; tt = 2; sub = 1; break;
+                    case FL_T_W2: m = &e->tc_w2[layer]; kindk = RK_W2; break;
+                    case FL_T_CLS: m = &e->tc_cls; kindk = RK_CLS; break;
+                }
+                if (gs == 64) pack_tc_kernel<64><<<dim3(e->n_sms, 16), 256, 0, e->stream>>>(e->staging, d_scales, m->d, e->tc_off[kindk], m_total, cols, row_base, rows, tt, sub);
+                else pack_tc_kernel<32><<<dim3(e->n_sms, 16), 256, 0, e->stream>>>(e->staging, d_scales, m->d, e->tc_off[kindk], m_total, cols, row_base, rows, tt, sub);
+            }
             if (e->want_mega) {
                 RkMat* m = nullptr;
                 int kindk = 0, m_total = rows, row_base = 0, tt = 1, sub = 0;
@@ -778,6 +1006,12 @@ int fl_finalize(fl_engine* e) {
     return FL_OK;
 }
 
+// copy `n` row descriptors to the device (pinned staging; the previous pass has been enqueued on the same stream)
+static int push_rows(fl_engine* e, int n) {
+    CK(e, cudaMemcpyAsync(e->rows, e->h_rows, sizeof(RowMeta) * n, cudaMemcpyHostToDevice, e->stream));
+    return FL_OK;
+}
+
 int fl_forward(fl_engine* e, int seq_slot, const int32_t* tokens, int n_tokens, int pos, float* logits_out, int32_t* argmax_out) {
     if (!e || !tokens) return set_err(e, FL_ERR_INVALID, "fl_forward: null argument");
     if (!e->finalized) return set_err(e, FL_ERR_INVALID, "fl_forward: call fl_finalize first");
@@ -788,18 +1022,36 @@ int fl_forward(fl_engine* e, int seq_slot, const int32_t* tokens, int n_tokens, 
     for (int i = 0; i < n_tokens; ++i)
         if (tokens[i] < 0 || tokens[i] >= c.vocab_size) return set_err(e, FL_ERR_INVALID, "fl_forward: token id %d out of range", tokens[i]);
     CK(e, cudaSetDevice(e->device));
-    memcpy(e->h_tokens, tokens, sizeof(int) * n_tokens);
-    CK(e, cudaMemcpyAsync(e->in_tokens, e->h_tokens, sizeof(int) * n_tokens, cudaMemcpyHostToDevice, e->stream));
-    // Prefill runs the tokens one position at a time: bit-identical to the reference's bs>1 forward, whose
-    // per-row arithmetic does not depend on the other rows (DESIGN.md "Prefill").
-    for (int i = 0; i < n_tokens; ++i) {
-        // n_out restarts at the last token of the call, so out_tokens[0] is the token sampled after the whole input
-        set_state_kernel<<<1, 1, 0, e->stream>>>(e->states + seq_slot, e->in_tokens, i, pos + i, n_tokens, i == n_tokens - 1);
-        e->launches += 1;
-        int rc = run_step(e, seq_slot);
-        if (rc) return rc;
+    const float* logits_src = e->logits;
+    if (e->tc && n_tokens > 1) {
+        // Prompt chunks on the tensor cores: up to kMaxRows tokens per weight pass (the reference forwards a prompt as batched
+        // forward() calls too, transformer.cpp:105-151; a row's arithmetic does not depend on the rows travelling with it).
+        for (int c0 = 0; c0 < n_tokens; c0 += kMaxRows) {
+            const int T = n_tokens - c0 < kMaxRows ? n_tokens - c0 : kMaxRows;
+            const bool last = c0 + T == n_tokens;
+            if (c0 > 0) CK(e, cudaStreamSynchronize(e->stream));        // the pinned row table is being reused
+            for (int i = 0; i < T; ++i) e->h_rows[i] = RowMeta{tokens[c0 + i], seq_slot, pos + c0 + i, n_tokens};
+            int rc = push_rows(e, T);
+            if (!rc) rc = enqueue_rows(e, T, last ? 1 : 0, 1, 1, e->stream);
+            if (rc) return rc;
+        }
+        logits_src = e->blogits;
+    } else {
+        memcpy(e->h_tokens, tokens, sizeof(int) * n_tokens);
+        CK(e, cudaMemcpyAsync(e->in_tokens, e->h_tokens, sizeof(int) * n_tokens, cudaMemcpyHostToDevice, e->stream));
+        // token by token: bit-identical to the reference's bs > 1 forward, whose per-row arithmetic does not depend on the other rows
+        for (int i = 0; i < n_tokens; ++i) {
+            // n_out restarts at the last token of the call, so out_tokens[0] is the token sampled after the whole input
+            set_state_kernel<<<1, 1, 0, e->stream>>>(e->states + seq_slot, e->in_tokens, i, pos + i, n_tokens, i == n_tokens - 1);
+            e->launches += 1;
+            int rc = run_step(e, seq_slot);
+            if (rc) return rc;
+        }
+        e->tap_rows = false;
     }
-    if (logits_out) CK(e, cudaMemcpyAsync(e->h_logits, e->logits, sizeof(float) * c.vocab_size, cudaMemcpyDeviceToHost, e->stream));
+    e->h_pos[seq_slot] = pos + n_tokens;
+    if (logits_out) CK(e, cudaMemcpyAsync(e->h_logits, logits_src, sizeof(float) * c.vocab_size, cudaMemcpyDeviceToHost, e->stream));
+    if (logits_src != e->logits) CK(e, cudaMemcpyAsync(e->logits, logits_src, sizeof(float) * c.vocab_size, cudaMemcpyDeviceToDevice, e->stream));
     if (argmax_out) CK(e, cudaMemcpyAsync(e->h_argmax, e->argmax_dev + seq_slot, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
     CK(e, cudaStreamSynchronize(e->stream));
     if (logits_out) memcpy(logits_out, e->h_logits, sizeof(float) * c.vocab_size);
@@ -817,8 +1069,20 @@ int fl_forward_batch(fl_engine* e, int n_seqs, const int32_t* tokens, const int3
             return set_err(e, FL_ERR_INVALID, "fl_forward_batch: sequence %d: token %d / pos %d out of range", i, tokens[i], pos[i]);
         e->h_tokens[i] = tokens[i];
     }
+    if (e->tc && n_seqs > 1) {
+        // ONE weight pass per step for all sequences (up to kMaxRows per pass): the projections are the M = n_seqs contraction
+        // of SURVEY 8(d) on the tensor cores; per-sequence results are bit-identical to fl_forward on that sequence alone
+        for (int s0 = 0; s0 < n_seqs; s0 += kMaxRows) {
+            const int T = n_seqs - s0 < kMaxRows ? n_seqs - s0 : kMaxRows;
+            if (s0 > 0) CK(e, cudaStreamSynchronize(e->stream));
+            for (int i = 0; i < T; ++i) e->h_rows[i] = RowMeta{tokens[s0 + i], s0 + i, pos[s0 + i], 1};
+            int rc = push_rows(e, T);
+            if (!rc) rc = enqueue_rows(e, T, T, 1, 0, e->stream);
+            if (rc) return rc;
+        }
+    } else {
     CK(e, cudaMemcpyAsync(e->in_tokens, e->h_tokens, sizeof(int) * n_seqs, cudaMemcpyHostToDevice, e->stream));
-    if (e->use_mega && n_seqs > 1 && !getenv("FL_NO_MULTISEQ")) {
+    if (e->use_mega && n_seqs > 1) {
         // one persistent launch per group of up to kMaxSeqsPerLaunch sequences: every phase is walked once per sequence, so the
         // exchanges and serial sections of one sequence hide behind the weight streaming of the others
         for (int i = 0; i < n_seqs; ++i) {
@@ -838,16 +1102,67 @@ int fl_forward_batch(fl_engine* e, int n_seqs, const int32_t* tokens, const int3
             if (rc) return rc;
         }
     }
+    e->tap_rows = false;
+    }
+    for (int i = 0; i < n_seqs; ++i) e->h_pos[i] = pos[i] + 1;
     if (argmax_out) CK(e, cudaMemcpyAsync(e->h_argmax, e->argmax_dev, sizeof(int) * n_seqs, cudaMemcpyDeviceToHost, e->stream));
     CK(e, cudaStreamSynchronize(e->stream));
     if (argmax_out) memcpy(argmax_out, e->h_argmax, sizeof(int) * n_seqs);
     return FL_OK;
 }
 
+// n_steps greedy steps of sequences 0 .. n_seqs-1 from their device-resident states (set by fl_forward / fl_forward_batch),
+// asynchronously on the engine stream: per step one captured graph = rows from the states, one weight pass, argmax + advance.
+int fl_decode_batch_async(fl_engine* e, int n_seqs, int n_steps) {
+    if (!e || !e->finalized) return set_err(e, FL_ERR_INVALID, "fl_decode_batch_async: engine not ready");
+    if (!e->tc) return set_err(e, FL_ERR_UNSUPPORTED, "fl_decode_batch_async: needs the tensor-core path (INT8, FL_FLAG_NO_TC clear)");
+    if (n_seqs < 1 || n_seqs > e->c.max_seqs || n_seqs > kMaxRows || n_steps < 0)
+        return set_err(e, FL_ERR_INVALID, "fl_decode_batch_async: n_seqs %d (max %d) / n_steps %d", n_seqs, e->c.max_seqs < kMaxRows ? e->c.max_seqs : kMaxRows, n_steps);
+    for (int i = 0; i < n_seqs; ++i)
+        if (e->h_pos[i] + n_steps > e->c.max_seq_len)
+            return set_err(e, FL_ERR_INVALID, "fl_decode_batch_async: sequence %d at position %d + %d steps exceeds max_seq_len %d", i, e->h_pos[i], n_steps, e->c.max_seq_len);
+    CK(e, cudaSetDevice(e->device));
+    const bool pdl = !(e->c.flags & FL_FLAG_NO_PDL);
+    auto enqueue = [&]() -> int {
+        int rc = launch_pdl(e, pdl, rows_from_states_kernel, dim3(1), dim3(kMaxRows), 0, e->stream, (const SeqState*)e->states, e->rows, n_seqs);
+        if (!rc) rc = enqueue_rows(e, n_seqs, n_seqs, 1, 0, e->stream);
+        return rc;
+    };
+    for (int s = 0; s < n_steps; ++s) {
+        if (e->c.flags & FL_FLAG_NO_GRAPH) {
+            if (int rc = enqueue()) return rc;
+            continue;
+        }
+        cudaGraphExec_t& ge = e->batch_graphs[n_seqs];
+        if (!ge) {
+            cudaGraph_t graph = nullptr;
+            const int64_t before = e->launches;
+            CK(e, cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+            int rc = enqueue();
+            cudaError_t st = cudaStreamEndCapture(e->stream, &graph);
+            e->kernels_per_step = (int)(e->launches - before);
+            e->launches = before;
+            if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+            if (st != cudaSuccess) return set_err(e, FL_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(st));
+            st = cudaGraphInstantiate(&ge, graph, 0);
+            cudaGraphDestroy(graph);
+            if (st != cudaSuccess) { ge = nullptr; return set_err(e, FL_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(st)); }
+        }
+        CK(e, cudaGraphLaunch(ge, e->stream));
+        e->launches += e->kernels_per_step;
+    }
+    for (int i = 0; i < n_seqs; ++i) e->h_pos[i] += n_steps;
+    return FL_OK;
+}
+
 int fl_decode_async(fl_engine* e, int seq_slot, int n_steps) {
     if (!e || !e->finalized) return set_err(e, FL_ERR_INVALID, "fl_decode_async: engine not ready");
     if (seq_slot < 0 || seq_slot >= e->c.max_seqs || n_steps < 0) return set_err(e, FL_ERR_INVALID, "fl_decode_async: bad argument");
+    if (e->h_pos[seq_slot] + n_steps > e->c.max_seq_len)
+        return set_err(e, FL_ERR_INVALID, "fl_decode_async: position %d + %d steps exceeds max_seq_len %d", e->h_pos[seq_slot], n_steps, e->c.max_seq_len);
     CK(e, cudaSetDevice(e->device));
+    e->h_pos[seq_slot] += n_steps;
+    e->tap_rows = false;
     if (e->use_mega) return n_steps > 0 ? launch_mega(e, seq_slot, n_steps) : FL_OK;   // all steps inside one persistent launch
     for (int i = 0; i < n_steps; ++i) {
         int rc = run_step(e, seq_slot);
@@ -1013,6 +1328,15 @@ int fl_generate(fl_engine* e, int seq_slot, const int32_t* prompt, int n_prompt,
     return rc;
 }
 
+// the first n tokens sampled for `seq_slot` since its last prefill (out_tokens[0] is the token sampled after the prompt)
+int fl_read_out_tokens(fl_engine* e, int seq_slot, int n, int32_t* out) {
+    if (!e || !out || seq_slot < 0 || seq_slot >= e->c.max_seqs || n < 0 || n > e->out_cap) return set_err(e, FL_ERR_INVALID, "fl_read_out_tokens: bad argument");
+    CK(e, cudaSetDevice(e->device));
+    CK(e, cudaStreamSynchronize(e->stream));
+    CK(e, cudaMemcpy(out, e->out_tokens + (size_t)seq_slot * e->out_cap, sizeof(int) * n, cudaMemcpyDeviceToHost));
+    return FL_OK;
+}
+
 void* fl_stream(fl_engine* e) { return e ? (void*)e->stream : nullptr; }
 
 int fl_sync(fl_engine* e) {
@@ -1082,7 +1406,11 @@ int fl_tap(fl_engine* e, const char* name, float* out, int cap) {
     CK(e, cudaSetDevice(e->device));
     CK(e, cudaStreamSynchronize(e->stream));
     const uint2* tagged = nullptr;       // the persistent kernel keeps these vectors as (value, tag) words
-    if (e->use_mega) {
+    if (e->tap_rows) {                   // the last forward ran on the rows path: its last row
+        if (!strcmp(name, "x1")) src = e->bx1 + (size_t)e->tap_row * c.dim;
+        else if (!strcmp(name, "attn")) src = e->batt + (size_t)e->tap_row * c.dim;
+        else if (!strcmp(name, "hd")) src = e->bhd + (size_t)e->tap_row * c.hidden_dim;
+    } else if (e->use_mega) {
         if (!strcmp(name, "x1")) tagged = e->x1t;
         else if (!strcmp(name, "attn")) tagged = e->attnt;
         else if (!strcmp(name, "hd")) tagged = e->hdt;
@@ -1191,6 +1519,61 @@ int fl_op_matmul_q(int quant_type, int group_size, const void* w, const float* w
         rc = launch_gemv<PRO_LOADQ, EPI_STORE>(nullptr, quant_type, group_size, a, grid, 0);
         if (rc) return rc;
     }
+    CKO(cudaDeviceSynchronize());
+    CKO(cudaMemcpy(out, dout.p, (size_t)rows_x * m * 4, cudaMemcpyDeviceToHost));
+    return FL_OK;
+}
+
+// quant::matmul on the tensor cores (tc_gemm.cuh), INT8 only: out[i*m + j] = W[j,:] . X[i,:] for rows_x <= 64 activation rows.
+// w3 != NULL: the fused W1/W3 pass, out = swiglu(W X, W3 X) (x86_simd.cpp:1766-1770).  variant: debugging knobs of the kernel.
+int fl_op_matmul_q_tc(int group_size, const void* w, const float* w_scales, const void* w3, const float* w3_scales, int m, int n,
+                      const void* x, const float* x_scales, int rows_x, float* out, int variant) {
+    if (!w || !w_scales || !x || !x_scales || !out || m < 1 || n < group_size || n % group_size || rows_x < 1 || rows_x > kMaxRows || (w3 && !w3_scales))
+        return set_err(nullptr, FL_ERR_INVALID, "fl_op_matmul_q_tc: bad argument");
+    if (group_size != 64 && group_size != 32) return set_err(nullptr, FL_ERR_UNSUPPORTED, "fl_op_matmul_q_tc: group size %d", group_size);
+    if (int rc = need_device()) return rc;
+    int dev = 0, sms = 148, max_smem = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    const int G = n / group_size, tt = w3 ? 2 : 1, N = tc_pad_n(rows_x), nkc = ceil_div(n, kTcKC);
+    std::vector<unsigned long long> off(sms + 1, 0);
+    for (int c = 0; c < sms; ++c) {
+        const TcPart pt = tc_part(m, c, sms);
+        unsigned long long bytes = 0;
+        for (int t = 0; t < pt.nt; ++t) { int lr0, R; tc_tile(pt, t, lr0, R); bytes += (unsigned long long)nkc * tc_stage_a_bytes(R, tt, group_size); }
+        off[c + 1] = off[c] + bytes;
+    }
+    DevBuf dw, dws, dw3, dws3, dp, doff, dx, dxs, dimg, dout;
+    const size_t img_bytes = tc_image_bytes(n, N, group_size);
+    if (dw.alloc((size_t)m * n) || dws.alloc((size_t)m * G * 4) || dp.alloc(off[sms] + 4096) || doff.alloc(sizeof(unsigned long long) * (sms + 1)) ||
+        dx.alloc((size_t)rows_x * n) || dxs.alloc((size_t)rows_x * G * 4) || dimg.alloc(img_bytes) || dout.alloc((size_t)rows_x * m * 4) ||
+        (w3 && (dw3.alloc((size_t)m * n) || dws3.alloc((size_t)m * G * 4))))
+        return set_err(nullptr, FL_ERR_OOM, "fl_op_matmul_q_tc: cudaMalloc");
+    CKO(cudaMemcpy(dw.p, w, (size_t)m * n, cudaMemcpyHostToDevice));
+    CKO(cudaMemcpy(dws.p, w_scales, (size_t)m * G * 4, cudaMemcpyHostToDevice));
+    if (w3) { CKO(cudaMemcpy(dw3.p, w3, (size_t)m * n, cudaMemcpyHostToDevice)); CKO(cudaMemcpy(dws3.p, w3_scales, (size_t)m * G * 4, cudaMemcpyHostToDevice)); }
+    CKO(cudaMemcpy(doff.p, off.data(), sizeof(unsigned long long) * (sms + 1), cudaMemcpyHostToDevice));
+    CKO(cudaMemcpy(dx.p, x, (size_t)rows_x * n, cudaMemcpyHostToDevice));
+    CKO(cudaMemcpy(dxs.p, x_scales, (size_t)rows_x * G * 4, cudaMemcpyHostToDevice));
+    CKO(cudaMemset(dp.p, 0, off[sms] + 4096));
+    CKO(cudaMemset(dimg.p, 0, img_bytes));
+    CKO(cudaMemset(dout.p, 0, (size_t)rows_x * m * 4));
+    if (group_size == 64) {
+        pack_tc_kernel<64><<<dim3(sms, 16), 256>>>(dw.as<uint8_t>(), dws.as<float>(), dp.as<uint8_t>(), doff.as<unsigned long long>(), m, n, 0, m, tt, 0);
+        if (w3) pack_tc_kernel<64><<<dim3(sms, 16), 256>>>(dw3.as<uint8_t>(), dws3.as<float>(), dp.as<uint8_t>(), doff.as<unsigned long long>(), m, n, 0, m, tt, 1);
+        tc_pack_x_kernel<64><<<256, 256>>>(dx.as<int8_t>(), dxs.as<float>(), dimg.as<uint8_t>(), rows_x, n, N);
+    } else {
+        pack_tc_kernel<32><<<dim3(sms, 16), 256>>>(dw.as<uint8_t>(), dws.as<float>(), dp.as<uint8_t>(), doff.as<unsigned long long>(), m, n, 0, m, tt, 0);
+        if (w3) pack_tc_kernel<32><<<dim3(sms, 16), 256>>>(dw3.as<uint8_t>(), dws3.as<float>(), dp.as<uint8_t>(), doff.as<unsigned long long>(), m, n, 0, m, tt, 1);
+        tc_pack_x_kernel<32><<<256, 256>>>(dx.as<int8_t>(), dxs.as<float>(), dimg.as<uint8_t>(), rows_x, n, N);
+    }
+    CKO(cudaGetLastError());
+    TcGemmArgs a{};
+    a.w = dp.as<uint8_t>(); a.cta_off = doff.as<unsigned long long>(); a.xq = dimg.as<uint8_t>(); a.out = dout.as<float>();
+    a.M = m; a.K = n; a.T = rows_x; a.ldo = m; a.smem_bytes = max_smem - 28 * 1024; a.variant = variant;
+    int rc = launch_qgemm(nullptr, false, group_size, N, w3 ? TC_EPI_SWIGLU : TC_EPI_STORE, a, sms, 0);
+    if (rc) return rc;
     CKO(cudaDeviceSynchronize());
     CKO(cudaMemcpy(out, dout.p, (size_t)rows_x * m * 4, cudaMemcpyDeviceToHost));
     return FL_OK;

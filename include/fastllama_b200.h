@@ -77,9 +77,10 @@ typedef struct {
 } fl_config;
 
 #define FL_FLAG_NO_GRAPH   1   /* launch kernels directly instead of replaying the captured CUDA graph */
-#define FL_FLAG_NO_PDL     2   /* reserved */
+#define FL_FLAG_NO_PDL     2   /* rows path: plain stream order instead of programmatic dependent launch between its kernels */
 #define FL_FLAG_PROFILE    8   /* persistent kernel records per-CTA time per category (fl_profile_read) */
 #define FL_FLAG_NO_MEGAKERNEL 4 /* run the step as separate kernels (one per phase) instead of the persistent decode kernel */
+#define FL_FLAG_NO_TC      16  /* never use the tensor-core rows path (tcgen05 GEMM): prompts and sequence batches go token by token */
 
 /* ---- lifecycle ---------------------------------------------------------------------------- */
 int  fl_create(const fl_config* cfg, int device, fl_engine** out);
@@ -105,6 +106,14 @@ int  fl_forward(fl_engine* e, int seq_slot, const int32_t* tokens, int n_tokens,
  * every phase is walked once per sequence, each with its own cache slot and position; per-sequence results are
  * bit-identical to fl_forward on that sequence alone.  Logits are not kept in this mode (token ids only). */
 int  fl_forward_batch(fl_engine* e, int n_seqs, const int32_t* tokens, const int32_t* pos, int32_t* argmax_out);
+
+/* n_steps greedy decode steps of sequences 0..n_seqs-1 (n_seqs <= 64) from their device-resident states, asynchronously on
+ * the engine stream: per step ONE weight pass for all sequences on the tensor cores (tcgen05 group-scaled INT8 GEMM), tokens fed
+ * back on the device, the step replayed as one CUDA graph.  INT8 engines only.  Results per sequence are bit-identical to
+ * fl_forward on that sequence alone. */
+int  fl_decode_batch_async(fl_engine* e, int n_seqs, int n_steps);
+/* the first n tokens sampled for seq_slot since its last prefill (waits for the engine stream) */
+int  fl_read_out_tokens(fl_engine* e, int seq_slot, int n, int32_t* out);
 
 /* Greedy generation with the token fed back on the device (no host round trip per token):
  * prefill `prompt`, then up to max_new tokens; stops after token id 0 (transformer.cpp:93).
@@ -164,6 +173,12 @@ int  fl_op_quantize(int quant_type, int group_size, const float* x, int n, void*
 /* quant::matmul (quant_operators.cpp:252-284): out[i*m + j] = W[j,:] . X[i,:] */
 int  fl_op_matmul_q(int quant_type, int group_size, const void* w, const float* w_scales, int m, int n,
                     const void* x, const float* x_scales, int rows_x, float* out);
+/* quant::matmul (quant_operators.cpp:252-284) for up to 64 activation rows in ONE weight pass on the tensor cores (INT8;
+ * tcgen05.mma.kind::i8 per quantisation group, FP32 group chain in the reference's order: bit-identical to fl_op_matmul_q).
+ * w3 / w3_scales non-NULL: the fused W1/W3 pass of execute_ffn13 (transformer.cpp:468-483), out = swiglu(W X, W3 X).
+ * variant: 0 (debugging knobs of the kernel otherwise). */
+int  fl_op_matmul_q_tc(int group_size, const void* w, const float* w_scales, const void* w3, const float* w3_scales, int m, int n,
+                       const void* x, const float* x_scales, int rows_x, float* out, int variant);
 /* simd::rmsnorm (x86_simd.cpp:1754-1764) */
 int  fl_op_rmsnorm(const float* x, const float* w, int n, float* out);
 /* rope_v2 (tf_operators.cpp:355-402) on one head vector */
