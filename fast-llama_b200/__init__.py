@@ -11,7 +11,7 @@ The directory name has a hyphen (the repo's required layout); import it with
 """
 from .binding import (Engine, Sampler, FlConfig, FlError, lib, lib_path, Q_INT8, Q_INT16,
                       T_TOK_EMB, T_ATT_NORM, T_WQ, T_WK, T_WV, T_WO, T_FFN_NORM, T_W1, T_W2, T_W3, T_OUT_NORM, T_CLS,
-                      FLAG_NO_GRAPH, FLAG_NO_PDL, FLAG_NO_MEGAKERNEL, FLAG_PROFILE, FLAG_NO_TC, ops, EXPORTED_SYMBOLS)
+                      FLAG_NO_GRAPH, FLAG_NO_PDL, FLAG_NO_MEGAKERNEL, FLAG_PROFILE, FLAG_NO_TC, FLAG_RELAXED, ops, EXPORTED_SYMBOLS)
 
 from . import shard, loaders, flm, gguf_file, tokenizer, convert
 from .generate import generate_text

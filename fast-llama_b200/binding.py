@@ -8,7 +8,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 Q_INT16, Q_INT8 = 1, 2
 (T_TOK_EMB, T_ATT_NORM, T_WQ, T_WK, T_WV, T_WO, T_FFN_NORM, T_W1, T_W2, T_W3, T_OUT_NORM, T_CLS) = range(12)
-FLAG_NO_GRAPH, FLAG_NO_PDL, FLAG_NO_MEGAKERNEL, FLAG_PROFILE, FLAG_NO_TC = 1, 2, 4, 8, 16
+FLAG_NO_GRAPH, FLAG_NO_PDL, FLAG_NO_MEGAKERNEL, FLAG_PROFILE, FLAG_NO_TC, FLAG_RELAXED = 1, 2, 4, 8, 16, 32
 
 EXPORTED_SYMBOLS = [
     "fl_create", "fl_destroy", "fl_last_error", "fl_upload", "fl_finalize", "fl_forward", "fl_forward_batch",

@@ -352,7 +352,9 @@ int enqueue_step(fl_engine* e, int slot, cudaStream_t st, int* n_kernels) {
 
 // multi = true: the variant that walks several sequences per phase (fl_forward_batch)
 template <typename F>
-int dispatch_mega(int qt, int gs, int hs, bool multi, F&& f) {
+int dispatch_mega(int qt, int gs, int hs, bool multi, F&& f, bool relaxed = false) {
+    // FL_FLAG_RELAXED: only the benchmark shape is instantiated (INT8, group 64, head 128, one sequence per launch)
+    if (relaxed && !multi && qt == FL_Q_INT8 && gs == 64 && hs == 128) return f(decode_megakernel<Q_INT8, 64, 128, false, true>);
 #define FL_MEGA_CASE(QT_, QTC, GS_, HS_) \
     if (qt == QT_ && gs == GS_ && hs == HS_) return multi ? f(decode_megakernel<QTC, GS_, HS_, true>) : f(decode_megakernel<QTC, GS_, HS_, false>);
     FL_MEGA_CASE(FL_Q_INT8, Q_INT8, 64, 128)
@@ -411,7 +413,10 @@ int setup_mega(fl_engine* e) {
     const int cph = e->cph;
     p.cph = cph;
     const int dw = c.head_size / cph;
-    const int v_chunk_bytes = getenv("FL_VCHUNK") ? atoi(getenv("FL_VCHUNK")) : 16384;     // tuning knob (profiles/r01: PV costs ~0.45 us per chunk on top of the chain; 4 KB 178, 8 KB 138, 16 KB 122 us per token)
+    int v_chunk_bytes = 16384;            // profiles/r01: PV costs ~0.45 us per chunk on top of the chain; 4 KB 178, 8 KB 138, 16 KB 122 us per token
+#ifdef FL_PROFILE                         // tuning knobs exist in the profiling build only (libfastllama_b200_prof.so)
+    if (getenv("FL_VCHUNK")) v_chunk_bytes = atoi(getenv("FL_VCHUNK"));
+#endif
     p.v_chunk_rows = v_chunk_bytes / 4 / dw;          // V chunks of 16 KB: rows x dims-per-part fp32
     // shared memory carve-up
     const int kmax = c.dim > c.hidden_dim ? c.dim : c.hidden_dim;
@@ -446,8 +451,10 @@ int setup_mega(fl_engine* e) {
     p.n_slots = n_slots;
     p.window = 99;
     p.debug_skip = 0;
-    if (const char* w = getenv("FL_DEBUG_SKIP")) p.debug_skip = atoi(w);      // timing experiments only: results are garbage
+#ifdef FL_PROFILE                         // the profiling build only: FL_DEBUG_SKIP makes results garbage by design
+    if (const char* w = getenv("FL_DEBUG_SKIP")) p.debug_skip = atoi(w);      // timing experiments only
     if (const char* w = getenv("FL_WINDOW")) { const int v = atoi(w); if (v >= 1) p.window = v; }      // tuning knob (profiles/)
+#endif
     p.off_bars = (int)off; off += al((size_t)n_slots * 16, 128);
     p.off_ring = (int)off; off += (size_t)n_slots * slot_bytes;
     e->mega_smem = off;
@@ -463,6 +470,7 @@ int setup_mega(fl_engine* e) {
         return FL_OK;
     };
     int rc = dispatch_mega(qt, gs, c.head_size, false, prepare);
+    if (rc == FL_OK && (c.flags & FL_FLAG_RELAXED)) rc = dispatch_mega(qt, gs, c.head_size, false, prepare, true);
     if (rc == FL_OK && c.max_seqs > 1) rc = dispatch_mega(qt, gs, c.head_size, true, prepare);
     if (rc == FL_ERR_UNSUPPORTED) return set_err(e, rc, "megakernel: unsupported quant/group/head combination");
     return rc;
@@ -485,8 +493,15 @@ int launch_mega(fl_engine* e, int slot, int n_steps, int n_seqs = 1) {
         auto sh = [&](auto*& ptr) { ptr = reinterpret_cast<std::remove_reference_t<decltype(ptr)>>(reinterpret_cast<uint8_t*>(ptr) + o); };
         sh(p.x1t); sh(p.qkvt); sh(p.attnt); sh(p.hdt); sh(p.score_t); sh(p.am);
     }
+    const uint64_t tags = (uint64_t)n_steps * (uint64_t)(c.n_layers + 1) * kTagsPerLayer;
+    if ((uint64_t)e->epoch + tags >= 0xfff00000ull) {
+        // the 32-bit tag space is about to wrap (~16 M tokens of a 32-layer model): start over with cleared exchange buffers
+        // (tag 0 is never used); ordered on the engine stream like every launch
+        CK(e, cudaMemsetAsync(e->xchg, 0, e->xchg_stride * c.max_seqs, e->stream));
+        e->epoch = 0;
+    }
     p.epoch = e->epoch;
-    e->epoch += (uint32_t)n_steps * (uint32_t)(c.n_layers + 1) * kTagsPerLayer;
+    e->epoch += (uint32_t)tags;
     return dispatch_mega(c.quant_type, c.group_size, c.head_size, n_seqs > 1, [&](auto kern) -> int {
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(e->n_sms); cfg.blockDim = dim3(kMegaThreads); cfg.dynamicSmemBytes = e->mega_smem; cfg.stream = e->stream;
@@ -498,7 +513,7 @@ int launch_mega(fl_engine* e, int slot, int n_steps, int n_seqs = 1) {
         if (s != cudaSuccess) return set_err(e, FL_ERR_CUDA, "megakernel launch: %s", cudaGetErrorString(s));
         e->launches += 1;
         return FL_OK;
-    });
+    }, (c.flags & FL_FLAG_RELAXED) != 0);
 }
 
 int run_step(fl_engine* e, int slot) {
@@ -1375,6 +1390,7 @@ void* fl_device_ptr(fl_engine* e, const char* name, int seq_slot) {
     if (!strcmp(name, "argmax")) return e->argmax_dev + seq_slot;           // int32: last sampled token
     if (!strcmp(name, "out_tokens")) return e->out_tokens + (size_t)seq_slot * e->out_cap;
     if (!strcmp(name, "logits")) return e->logits;                          // fp32[vocab]
+    if (!strcmp(name, "gathered")) return e->ag_recv;                       // int32[world * n_local]: result of the last fl_allgather_tokens
     return nullptr;
 }
 
@@ -1443,17 +1459,27 @@ int fl_set_comm(fl_engine* e, void* nccl_comm, int rank, int world) {
 }
 
 int fl_allgather_tokens(fl_engine* e, const int32_t* local, int n_local, int32_t* all) {
-    if (!e || !local || !all || n_local < 1 || n_local > 1024 || e->world > 16) return set_err(e, FL_ERR_INVALID, "fl_allgather_tokens: bad argument");
-    if (e->world == 1) { memcpy(all, local, sizeof(int) * n_local); return FL_OK; }
-    auto fn = (nccl_allgather_fn)dlsym(e->nccl_lib, "ncclAllGather");
-    if (!fn) return set_err(e, FL_ERR_NCCL, "fl_allgather_tokens: ncclAllGather not found");
+    if (!e || n_local < 1 || n_local > 1024 || e->world > 16 || (local && !all)) return set_err(e, FL_ERR_INVALID, "fl_allgather_tokens: bad argument");
+    if (!local && n_local > e->c.max_seqs) return set_err(e, FL_ERR_INVALID, "fl_allgather_tokens: n_local %d > max_seqs %d", n_local, e->c.max_seqs);
     CK(e, cudaSetDevice(e->device));
-    CK(e, cudaMemcpyAsync(e->ag_send, local, sizeof(int) * n_local, cudaMemcpyHostToDevice, e->stream));
-    const int ncclInt32 = 2;
-    int rc = fn(e->ag_send, e->ag_recv, (size_t)n_local, ncclInt32, e->nccl_comm, e->stream);
-    if (rc != 0) return set_err(e, FL_ERR_NCCL, "ncclAllGather failed: %d", rc);
-    CK(e, cudaMemcpyAsync(all, e->ag_recv, sizeof(int) * n_local * e->world, cudaMemcpyDeviceToHost, e->stream));
-    CK(e, cudaStreamSynchronize(e->stream));
+    // local == NULL: the tokens just sampled on the device for slots 0 .. n_local-1 (no host round trip); the gathered tokens
+    // stay in device memory (fl_device_ptr "gathered") unless `all` is given
+    const int* src = local ? e->ag_send : e->argmax_dev;
+    if (local) CK(e, cudaMemcpyAsync(e->ag_send, local, sizeof(int) * n_local, cudaMemcpyHostToDevice, e->stream));
+    if (e->world == 1) {
+        CK(e, cudaMemcpyAsync(e->ag_recv, src, sizeof(int) * n_local, cudaMemcpyDeviceToDevice, e->stream));
+    } else {
+        auto fn = (nccl_allgather_fn)dlsym(e->nccl_lib, "ncclAllGather");
+        if (!fn) return set_err(e, FL_ERR_NCCL, "fl_allgather_tokens: ncclAllGather not found");
+        const int ncclInt32 = 2;
+        int rc = fn(src, e->ag_recv, (size_t)n_local, ncclInt32, e->nccl_comm, e->stream);
+        if (rc != 0) return set_err(e, FL_ERR_NCCL, "ncclAllGather failed: %d", rc);
+    }
+    e->launches += 1;
+    if (all) {
+        CK(e, cudaMemcpyAsync(all, e->ag_recv, sizeof(int) * n_local * e->world, cudaMemcpyDeviceToHost, e->stream));
+        CK(e, cudaStreamSynchronize(e->stream));
+    }
     return FL_OK;
 }
 

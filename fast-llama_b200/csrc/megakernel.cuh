@@ -430,7 +430,9 @@ __device__ __forceinline__ float sumsq_chain_t(const float* xt, int n, int lane)
 // flight before the first tag is looked at.  The rmsnorm case needs the whole vector before its scale is known, so it
 // must fit ONE batch (K <= 24 * 256 = 6144, checked by the host): the products x*w and the group maxima wait in
 // registers while warp 0 walks the sum-of-squares chain (max |(x*w)*r| == (max |x*w|)*r: rounding is monotonic, r > 0).
-template <int QT, int GS>
+// RX (FL_FLAG_RELAXED, measurement of what bit-exactness costs): the sum of squares is a tree reduction instead of the
+// reference's four 1024-step FMA chains - same value up to FP32 rounding (~1e-7 relative), NOT the reference's bits.
+template <int QT, int GS, bool RX = false>
 __device__ __forceinline__ void build_activation(uint8_t* xq, float* xs, float* xt, float* misc, const uint2* src, uint32_t tag,
                                                  const float* gain, int K, float* tap, int tid, Prof& pf, uint32_t* gate = nullptr, uint32_t gate_val = 0u) {
     using RK = Rk<QT, GS>;
@@ -502,6 +504,7 @@ __device__ __forceinline__ void build_activation(uint8_t* xq, float* xs, float* 
         }
         if (!gain && b0 + MAXP < n_pass) issue_batch(b0 + MAXP);
         float rr = 1.0f;
+        float ss_part = 0.0f;
         if (gain) {
             // raw x -> transposed image for the chain; products and group maxima stay in registers
 #pragma unroll
@@ -509,7 +512,10 @@ __device__ __forceinline__ void build_activation(uint8_t* xq, float* xs, float* 
                 const int g = g0 + (b0 + ps) * GPP;
                 if (b0 + ps < n_pass && g < G) {
                     const int e0 = g * GS + sub * PER;                   // multiple of 4
-                    if (PER == 8) {
+                    if (RX) {
+#pragma unroll
+                        for (int i = 0; i < PER; ++i) ss_part = __fmaf_rn(y[ps][i], y[ps][i], ss_part);
+                    } else if (PER == 8) {
 #pragma unroll
                         for (int j = 0; j < 4; ++j) *reinterpret_cast<float2*>(xt + j * (K >> 2) + (e0 >> 2)) = make_float2(y[ps][j], y[ps][(4 + j) % PER]);
                     } else {
@@ -534,7 +540,17 @@ __device__ __forceinline__ void build_activation(uint8_t* xq, float* xs, float* 
             }
             m[ps] = group_max8(mm);
         }
-        if (gain) {
+        if (gain && RX) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ss_part = __fadd_rn(ss_part, __shfl_xor_sync(kFull, ss_part, o));
+            if (lane == 0) misc[8 + warp] = ss_part;
+            consumer_sync();
+            float ss = misc[8];
+#pragma unroll
+            for (int w = 1; w < kConsumerWarps; ++w) ss = __fadd_rn(ss, misc[8 + w]);
+            rr = rms_scale(ss, K);
+            pf.stop(tid, 9);
+        } else if (gain) {
             consumer_sync();
             pf.stop(tid, 8);
             if (warp == kSerialWarp) {
@@ -642,7 +658,7 @@ __device__ __forceinline__ float pv_rows(const float* vb, const float* wp, int D
     return o;
 }
 
-template <int HS>
+template <int HS, bool RX = false>
 __device__ __forceinline__ void attention_part(const MegaParams& p, const SeqView sv, uint8_t* smem, int layer, int qh, int part, int pos, int bs,
                                                uint32_t tag_qkv, uint32_t tag_score, uint32_t tag_out, uint32_t phases_drained, int tid, Prof& pf,
                                                uint32_t* gate = nullptr, uint32_t gate_val = 0u) {
@@ -681,12 +697,17 @@ __device__ __forceinline__ void attention_part(const MegaParams& p, const SeqVie
         bulk_g2s(v_stage + (size_t)slot * VR * DW, vc + (size_t)c * VR * DW, bytes, &vfull[slot]);
     };
     if (tid < 32) slowbits[tid] = 0u;
+    // K/V rows of earlier tokens were appended by plain stores of another CTA (part 0 of this head); that CTA's chain warp
+    // fenced them before it published tagged rows this CTA has polled since (see the Wo epilogue).  Acquire side of that
+    // hand-off, before the cache is read through ld.cg (K) and through the async proxy (V bulk copies):
+    __threadfence();
     const int pvt = tid - (kConsumerThreads - DW);          // index inside the PV group (the last DW consumer threads), < 0 for the others
     if (pvt == 0) {
         // the ring also covers the pair buffers: wait until this CTA's chain warp has finished the QKV phase (it trails the
         // consumers by one superblock at most)
         while ((int)(ld_shared_volatile_u32(reinterpret_cast<uint32_t*>(smem + p.off_misc) + 29) - phases_drained) < 0) __nanosleep(50);
         fence_proxy_async();                                // the ring aliases memory the generic proxy wrote (activation image, pairs)
+        asm volatile("fence.proxy.async.global;" ::: "memory");      // the V rows were written through the generic proxy
         for (int c = 0; c < min(NCH, n_chunks); ++c) issue_v(c);
     }
 
@@ -817,7 +838,22 @@ __device__ __forceinline__ void attention_part(const MegaParams& p, const SeqVie
     for (int t = tid; t < n; t += kConsumerThreads) att[t] = expf_exact(__fsub_rn(att[t], m));
     if (tid < 8) att[n + tid] = 0.0f;                      // the chains below read whole float4s
     consumer_sync();
-    if (tid == kSerialWarp * 32) {
+    if (RX) {
+        // relaxed: per-thread partial sums, warp tree, 8 partials in order (not the reference's serial order)
+        float part = 0.0f;
+#pragma unroll 1
+        for (int t = tid; t < n; t += kConsumerThreads) part = __fadd_rn(part, att[t]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part = __fadd_rn(part, __shfl_xor_sync(kFull, part, o));
+        if (lane == 0) red[8 + warp] = part;
+        consumer_sync();
+        if (tid == 0) {
+            float tot = red[8];
+#pragma unroll
+            for (int w = 1; w < kConsumerWarps; ++w) tot = __fadd_rn(tot, red[8 + w]);
+            red[16] = tot;
+        }
+    } else if (tid == kSerialWarp * 32) {
         // one FP32 add chain in index order; loads run one batch ahead of the adds
         const float4* a4 = reinterpret_cast<const float4*>(att);
         const int nv = n >> 2;
@@ -891,7 +927,7 @@ __device__ __forceinline__ void attention_part(const MegaParams& p, const SeqVie
 }
 
 // ---------------------------------------------------------------------------------------------- the kernel
-template <int QT, int GS, int HS, bool MS = false>
+template <int QT, int GS, int HS, bool MS = false, bool RX = false>
 __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __grid_constant__ MegaParams p) {
     using RK = Rk<QT, GS>;
     const int n_seqs = MS ? p.n_seqs : 1;
@@ -1068,6 +1104,11 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
                     pf.log(lane, 9, 6, t);
                 }
                 __syncwarp();
+                // Release side of the KV-cache hand-off: this CTA's consumer warps appended the token's K/V rows during attention
+                // (plain stores, ordered before this point by the pair-buffer barriers).  The fence makes them visible
+                // device-wide before the tagged rows this warp publishes next (hd, then x1), which every CTA polls before it
+                // reads the cache for the next token.  Off the critical path: the Wo rows are already out.
+                if (pk == 1) __threadfence();
                 if (lane == 0) st_shared_volatile_u32(reinterpret_cast<uint32_t*>(smem + p.off_misc) + 29, ++phases_done);      // pair buffers are idle until the next drain
                 if (pk == 4) {
                     // per-CTA argmax partial (sampler.cpp:36-46: first index of the strict maximum)
@@ -1154,7 +1195,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
                 const uint32_t gpi = MS ? (uint32_t)((step * n_phases + pi) * n_seqs + sq) : (uint32_t)(step * n_phases + pi);
                 const bool no_attn_here = !(attn_cta && !(p.debug_skip & 8));
                 const uint32_t gate_val = gpi + ((!MS && pk == 0 && no_attn_here) ? 2u : 1u);
-                if (!(p.debug_skip & 8)) build_activation<QT, GS>(xq, xs, xt, misc, in, tag_in, gain, K, (pk == 4 && blockIdx.x == 0) ? p.tap_norm : nullptr, tid, pf,
+                if (!(p.debug_skip & 8)) build_activation<QT, GS, RX>(xq, xs, xt, misc, in, tag_in, gain, K, (pk == 4 && blockIdx.x == 0) ? p.tap_norm : nullptr, tid, pf,
                                                                   (!MS && pk == 1) ? nullptr : gate, gate_val);
             }
             pf.stop(tid, 1);
@@ -1267,7 +1308,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
                 for (int sq = 0; sq < n_seqs; ++sq) {
                     const int pos = (MS ? sstate[4 * sq + 2] : pos0) + step;
                     const int bs = step == 0 ? (MS ? sstate[4 * sq + 3] : bs0) : 1;
-                    attention_part<HS>(p, seq_view<MS>(p, sq), smem, layer, my_head, my_part, pos, bs, tl + 1u, tl + 2u, tl + 3u, phases_drained, tid, pf,
+                    attention_part<HS, RX>(p, seq_view<MS>(p, sq), smem, layer, my_head, my_part, pos, bs, tl + 1u, tl + 2u, tl + 3u, phases_drained, tid, pf,
                                        MS ? nullptr : reinterpret_cast<uint32_t*>(smem + p.off_misc) + 20, (uint32_t)(step * n_phases + pi) + 2u);
                 }
             }

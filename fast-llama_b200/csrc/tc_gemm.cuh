@@ -16,7 +16,8 @@
 // Roles (320 threads): warp 0 = bulk-copy producer (weights never depend on activations: under programmatic dependent
 // launch it fills the ring while the previous kernel is still running, and only then waits for the activations);
 // warp 1 = MMA issuer (one thread) + TMEM owner; warps 2-9 = two epilogue warpgroups.  TMEM holds up to 8 accumulator
-// buffers, so the MMAs of group g+1.. run while the chain of group g is walked.
+// "units" of a few groups each (one full/empty barrier pair per unit, not per group: the issuer thread and the epilogue
+// warps pay their synchronisation latency once per unit), so the MMAs of the next units run while a unit's chains are walked.
 //   W1/W3 (DUAL): the two matrices are separate MMAs of one stage into adjacent TMEM columns of the same lanes; warpgroup 0
 //   owns the W1 chains, warpgroup 1 the W3 chains, SwiGLU joins them through shared memory.
 //   otherwise the two warpgroups split the activation rows (columns) of one accumulator.
@@ -25,7 +26,7 @@
 
 namespace fl {
 
-constexpr int kTcKC = 128;               // bytes (= int8 elements) of K per stage
+constexpr int kTcKC = 256;               // bytes (= int8 elements) of K per stage
 constexpr int kTcThreads = 320;
 constexpr int kTcMaxRows = 128;          // rows per tile = MMA M
 constexpr int kTcMaxSlots = 12;
@@ -138,11 +139,15 @@ __device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo, uint32
 __host__ __device__ constexpr uint32_t tc_idesc_i8(int M, int N) {
     return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-__device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+// descriptors travel as (lo, hi) halves: hi (stride offset, version) is constant, lo = start address | leading offset << 16
+template <bool ACC>
+__device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
-        :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %4, {%6, %6, %6, %6}, p;\n\t}"
+        :: "r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "n"(ACC ? 1 : 0), "r"(0u) : "memory");
 }
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, int (&d)[16]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -173,19 +178,29 @@ struct TcGemmArgs {
     int T;                                 // live activation rows (<= N)
     int ldo;
     int smem_bytes;                        // dynamic shared memory handed to the launch
-    int variant;                           // debugging: bit 0 swap LBO/SBO in the descriptors
+    int variant;                           // reserved (0)
+};
+
+template <int GS, int N, bool DUAL>
+struct TcShape {
+    static constexpr int TT = DUAL ? 2 : 1;
+    static constexpr int GPS = kTcKC / GS;                 // groups per stage
+    static constexpr int MPG = GS / 32;                    // K = 32 MMAs per group
+    static constexpr int NB = TT * N;                      // TMEM columns per group
+    static constexpr int GU = (128 / NB) >= GPS ? GPS : ((128 / NB) >= 1 ? (128 / NB) : 1);     // groups per TMEM unit (<= 128 columns)
+    static constexpr int UPS = GPS / GU;                   // units per stage
+    static constexpr int NUNITS = (512 / (GU * NB)) > 8 ? 8 : (512 / (GU * NB));
+    static constexpr bool SPLIT = !DUAL && N >= 16;        // the two epilogue warpgroups share the columns of one accumulator
+    static constexpr int NC = (DUAL || !SPLIT) ? N : N / 2;   // columns (activation rows) per epilogue thread
+    static constexpr int EPW = (DUAL || SPLIT) ? 8 : 4;    // epilogue warps that take part
+    static_assert(GPS % GU == 0 && NUNITS >= 2, "unit geometry");
 };
 
 template <int GS, int N, bool DUAL, int EPI>
 __global__ void __launch_bounds__(kTcThreads, 1) qgemm_kernel(const __grid_constant__ TcGemmArgs a) {
-    constexpr int TT = DUAL ? 2 : 1;
-    constexpr int GPS = kTcKC / GS;                 // groups per stage
-    constexpr int MPG = GS / 32;                    // K = 32 MMAs per group
-    constexpr int NB = TT * N;                      // TMEM columns per accumulator buffer
-    constexpr int NBUF = (512 / NB) > 8 ? 8 : (512 / NB);
-    constexpr bool SPLIT = !DUAL && N >= 16;        // the two epilogue warpgroups share the columns of one accumulator
-    constexpr int NC = (DUAL || !SPLIT) ? N : N / 2;   // columns (activation rows) per epilogue thread
-    constexpr int EPW = (DUAL || SPLIT) ? 8 : 4;    // epilogue warps that take part
+    using S = TcShape<GS, N, DUAL>;
+    constexpr int TT = S::TT, GPS = S::GPS, MPG = S::MPG, NB = S::NB, GU = S::GU, UPS = S::UPS, NUNITS = S::NUNITS, NC = S::NC, EPW = S::EPW;
+    constexpr bool SPLIT = S::SPLIT;
     static_assert(!DUAL || EPI == TC_EPI_SWIGLU, "the fused W1/W3 stream ends in SwiGLU");
     static_assert(N == 8 || N == 16 || N == 32 || N == 64, "N");
 
@@ -212,7 +227,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) qgemm_kernel(const __grid_const
 
     if (tid == 0) {
         for (int i = 0; i < n_slots; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1 + EPW); }
-        for (int i = 0; i < NBUF; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], EPW); }
+        for (int i = 0; i < NUNITS; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], EPW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tc_alloc(tmem_slot, 512);
@@ -271,34 +286,44 @@ __global__ void __launch_bounds__(kTcThreads, 1) qgemm_kernel(const __grid_const
         // ================= MMA issuer =================
         if (lane == 0) {
             const uint32_t idesc = tc_idesc_i8(128, N);
-            uint32_t slot = 0, par = 0, buf = 0, bpar = 1;       // tempty parity 1 passes on a fresh barrier
+            const uint32_t desc_hi = (128u >> 4) | (1u << 14);       // stride (M/N) byte offset 128, descriptor version 1
+            uint32_t slot = 0, par = 0, un = 0, upar = 1;            // tempty parity 1 passes on a fresh barrier
             for (int t = 0; t < pt.nt; ++t) {
                 int lr0, R;
                 tc_tile(pt, t, lr0, R);
-                const uint32_t lbo_a = (uint32_t)R * 16u, lbo_b = (uint32_t)N * 16u;
+                const uint32_t lbo_a = (uint32_t)R, lbo_b = (uint32_t)N;     // leading (K) byte offsets / 16
                 for (int kc = 0; kc < nkc; ++kc) {
                     mbar_wait(&full[slot], par);
                     tc_fence_after();
-                    const uint32_t b_img = smem_u32(ring + (size_t)slot * slot_bytes);
-                    const uint32_t a_img = b_img + (uint32_t)b_bytes;
+                    const uint32_t b_img = (smem_u32(ring + (size_t)slot * slot_bytes) & 0x3ffffu) >> 4;     // in 16-byte units
+                    const uint32_t a_img = b_img + (uint32_t)(b_bytes >> 4);
                     const int ng = (Gtot - kc * GPS) < GPS ? (Gtot - kc * GPS) : GPS;
-                    for (int g = 0; g < ng; ++g) {
-                        mbar_wait(&tempty[buf], bpar);
-                        tc_fence_after();
 #pragma unroll
-                        for (int m = 0; m < TT; ++m) {
+                    for (int u = 0; u < UPS; ++u) {
+                        if (u * GU < ng) {
+                            mbar_wait(&tempty[un], upar);
+                            tc_fence_after();
 #pragma unroll
-                            for (int k32 = 0; k32 < MPG; ++k32) {
-                                const uint32_t k16 = (uint32_t)(g * (GS / 16) + k32 * 2);
-                                const uint32_t aa = a_img + (uint32_t)m * kTcKC * (uint32_t)R + k16 * lbo_a;
-                                const uint32_t bb = b_img + k16 * lbo_b;
-                                const uint64_t ad = (a.variant & 1) ? tc_desc(aa, 128u, lbo_a) : tc_desc(aa, lbo_a, 128u);
-                                const uint64_t bd = (a.variant & 1) ? tc_desc(bb, 128u, lbo_b) : tc_desc(bb, lbo_b, 128u);
-                                tc_mma_i8(tmem_base + buf * NB + (uint32_t)m * N, ad, bd, idesc, k32 > 0 ? 1u : 0u);
+                            for (int gg = 0; gg < GU; ++gg) {
+                                const int g = u * GU + gg;
+                                if (g < ng) {
+#pragma unroll
+                                    for (int m = 0; m < TT; ++m) {
+                                        const uint32_t dcol = tmem_base + un * (GU * NB) + (uint32_t)(gg * NB + m * N);
+#pragma unroll
+                                        for (int k32 = 0; k32 < MPG; ++k32) {
+                                            const uint32_t k16 = (uint32_t)(g * (GS / 16) + k32 * 2);
+                                            const uint32_t a_lo = (a_img + (uint32_t)m * (kTcKC / 16) * lbo_a + k16 * lbo_a) | (lbo_a << 16);
+                                            const uint32_t b_lo = (b_img + k16 * lbo_b) | (lbo_b << 16);
+                                            if (k32 == 0) tc_mma_i8<false>(dcol, a_lo, b_lo, desc_hi, idesc);
+                                            else tc_mma_i8<true>(dcol, a_lo, b_lo, desc_hi, idesc);
+                                        }
+                                    }
+                                }
                             }
+                            tc_commit(&tfull[un]);
+                            if (++un == (uint32_t)NUNITS) { un = 0; upar ^= 1u; }
                         }
-                        tc_commit(&tfull[buf]);
-                        if (++buf == (uint32_t)NBUF) { buf = 0; bpar ^= 1u; }
                     }
                     tc_commit(&empty[slot]);      // the stage's operands have been read once every MMA above has completed
                     if (++slot == (uint32_t)n_slots) { slot = 0; par ^= 1u; }
@@ -314,7 +339,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) qgemm_kernel(const __grid_const
         const int msel = DUAL ? wg : 0;                          // which matrix of the fused stream
         const uint32_t tcol = (uint32_t)(DUAL ? wg * N : c0);
         pdl_wait();                                              // RESADD reads `out`; every kernel of the chain waits
-        uint32_t slot = 0, par = 0, buf = 0, fpar = 0;
+        uint32_t slot = 0, par = 0, un = 0, fpar = 0;
         for (int t = 0; t < pt.nt; ++t) {
             int lr0, R;
             tc_tile(pt, t, lr0, R);
@@ -330,41 +355,59 @@ __global__ void __launch_bounds__(kTcThreads, 1) qgemm_kernel(const __grid_const
                 const float* xs_st = reinterpret_cast<const float*>(st + kTcKC * N);                              // [GPS][N]
                 const float* ws_st = reinterpret_cast<const float*>(st + b_bytes + TT * kTcKC * R) + msel * GPS * R; // [GPS][R]
                 const int ng = (Gtot - kc * GPS) < GPS ? (Gtot - kc * GPS) : GPS;
-                for (int g = 0; g < ng; ++g) {
-                    mbar_wait(&tfull[buf], fpar);
-                    tc_fence_after();
-                    if (quad_live) {
-                        const float ws = live ? ws_st[g * R + r] : 0.0f;
-                        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * NB + tcol;
-                        if (NC == 8) {
-                            int d[8];
-                            tc_ld8(taddr, d);
-                            tc_ld_wait();
-                            const float4 x0 = *reinterpret_cast<const float4*>(xs_st + g * N + c0), x1 = *reinterpret_cast<const float4*>(xs_st + g * N + c0 + 4);
-                            const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) acc[i] = __fmaf_rn(__fmul_rn(ws, xs[i]), __int2float_rn(d[i]), acc[i]);
-                        } else {
+                for (int u = 0; u < UPS; ++u) {
+                    if (u * GU < ng) {
+                        mbar_wait(&tfull[un], fpar);
+                        tc_fence_after();
+                        if (quad_live) {
+                            const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + un * (GU * NB) + tcol;
+                            if (NC == 8) {
+                                // all groups of the unit at once: GU x 8 columns, NB columns apart
+                                int d[GU][8];
 #pragma unroll
-                            for (int cb = 0; cb < NC; cb += 16) {
-                                int d[16];
-                                tc_ld16(taddr + (uint32_t)cb, d);
+                                for (int gg = 0; gg < GU; ++gg) tc_ld8(tbase + (uint32_t)(gg * NB), d[gg]);
                                 tc_ld_wait();
 #pragma unroll
-                                for (int i4 = 0; i4 < 16; i4 += 4) {
-                                    const float4 x = *reinterpret_cast<const float4*>(xs_st + g * N + c0 + cb + i4);
-                                    acc[cb + i4] = __fmaf_rn(__fmul_rn(ws, x.x), __int2float_rn(d[i4]), acc[cb + i4]);
-                                    acc[cb + i4 + 1] = __fmaf_rn(__fmul_rn(ws, x.y), __int2float_rn(d[i4 + 1]), acc[cb + i4 + 1]);
-                                    acc[cb + i4 + 2] = __fmaf_rn(__fmul_rn(ws, x.z), __int2float_rn(d[i4 + 2]), acc[cb + i4 + 2]);
-                                    acc[cb + i4 + 3] = __fmaf_rn(__fmul_rn(ws, x.w), __int2float_rn(d[i4 + 3]), acc[cb + i4 + 3]);
+                                for (int gg = 0; gg < GU; ++gg) {
+                                    const int g = u * GU + gg;
+                                    if (g < ng) {
+                                        const float ws = live ? ws_st[g * R + r] : 0.0f;
+                                        const float4 x0 = *reinterpret_cast<const float4*>(xs_st + g * N + c0), x1 = *reinterpret_cast<const float4*>(xs_st + g * N + c0 + 4);
+                                        const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+                                        for (int i = 0; i < 8; ++i) acc[i] = __fmaf_rn(__fmul_rn(ws, xs[i]), __int2float_rn(d[gg][i]), acc[i]);
+                                    }
+                                }
+                            } else {
+#pragma unroll
+                                for (int gg = 0; gg < GU; ++gg) {
+                                    const int g = u * GU + gg;
+                                    if (g < ng) {
+                                        const float ws = live ? ws_st[g * R + r] : 0.0f;
+#pragma unroll
+                                        for (int cb = 0; cb < NC; cb += 16) {
+                                            int d[16];
+                                            tc_ld16(tbase + (uint32_t)(gg * NB + cb), d);
+                                            tc_ld_wait();
+#pragma unroll
+                                            for (int i4 = 0; i4 < 16; i4 += 4) {
+                                                const float4 x = *reinterpret_cast<const float4*>(xs_st + g * N + c0 + cb + i4);
+                                                acc[cb + i4] = __fmaf_rn(__fmul_rn(ws, x.x), __int2float_rn(d[i4]), acc[cb + i4]);
+                                                acc[cb + i4 + 1] = __fmaf_rn(__fmul_rn(ws, x.y), __int2float_rn(d[i4 + 1]), acc[cb + i4 + 1]);
+                                                acc[cb + i4 + 2] = __fmaf_rn(__fmul_rn(ws, x.z), __int2float_rn(d[i4 + 2]), acc[cb + i4 + 2]);
+                                                acc[cb + i4 + 3] = __fmaf_rn(__fmul_rn(ws, x.w), __int2float_rn(d[i4 + 3]), acc[cb + i4 + 3]);
+                                            }
+                                        }
+                                    }
                                 }
                             }
                         }
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tempty[un]);          // the unit's values are in registers / consumed
+                        if (++un == (uint32_t)NUNITS) { un = 0; fpar ^= 1u; }
                     }
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&tempty[buf]);          // the accumulator's values are in registers
-                    if (++buf == (uint32_t)NBUF) { buf = 0; fpar ^= 1u; }
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[slot]);              // the stage's scales have been read

@@ -67,11 +67,16 @@ def permute_qk(w, n_heads, n_kv_heads=None):
 
 # ------------------------------------------------------------------------------------------------- writer
 class _Out:
-    def __init__(self):
-        self.parts, self.pos = [], 0
+    """byte sink that knows its position: in memory, or straight into a file (a 7B model is 7.4 GB)"""
+
+    def __init__(self, f=None):
+        self.parts, self.pos, self.f = [], 0, f
 
     def put(self, b):
-        self.parts.append(b)
+        if self.f is not None:
+            self.f.write(b)
+        else:
+            self.parts.append(b)
         self.pos += len(b)
 
     def bytes(self):
@@ -98,11 +103,14 @@ def _block(out, name, data, block_type, data_type=D_NONE, align=8, header_data=b
     header_size += _pad(out.pos + header_size, align)
     if header_size > 255:
         raise ValueError(f"block name {name!r} is too long")
-    tail = _pad(header_size + len(data), align)
-    head = struct.pack("<6BHQ", block_type, data_type, header_size, len(header_data), name_offset, len(nm), tail, len(data))
+    parts = data if isinstance(data, list) else [data]
+    n_data = sum(len(d) for d in parts)
+    tail = _pad(header_size + n_data, align)
+    head = struct.pack("<6BHQ", block_type, data_type, header_size, len(header_data), name_offset, len(nm), tail, n_data)
     head += header_data + nm + b"\0"
     out.put(head + b"\0" * (header_size - len(head)))
-    out.put(data)
+    for d in parts:
+        out.put(d)
     out.put(b"\0" * tail)
 
 
@@ -146,25 +154,30 @@ def _tokenizer_bytes(vocab):
 
 def write_flm(path, cfg, tensors, vocab=None, version=(1, 0, 0)):
     """cfg: dict with CONFIG_FIELDS keys; tensors: {(engine kind, layer): (payload ndarray, scales ndarray | None)}
-    (the layout quantize_rows / fl_upload use); vocab: see _tokenizer_bytes (None writes no tokenizer block).
+    (the layout quantize_rows / fl_upload use) or a callable (kind, layer) -> (payload, scales) that produces them on demand;
+    vocab: see _tokenizer_bytes (None writes no tokenizer block).
     Blocks are written in the converter's order: embedding, layers 0..L-1 (q k v o gate up down, the two norms),
-    output norm, classifier."""
-    out = _Out()
+    output norm, classifier, each straight into the file."""
+    with open(path, "wb") as f:
+        _write_flm(_Out(f), cfg, tensors, vocab, version)
+
+
+def _write_flm(out, cfg, tensors, vocab, version):
     out.put(struct.pack("<I2BH", FILE_TAG, *version))
     _block(out, "model_config", _config_bytes(cfg), B_DICT)
     if vocab is not None:
         _block(out, "tokenizer", _tokenizer_bytes(vocab), B_DICT)
 
     def tensor(kind, layer):
-        q, s = tensors[(kind, layer)]
+        q, s = tensors(kind, layer) if callable(tensors) else tensors[(kind, layer)]
         q = np.ascontiguousarray(q)
         tt = KIND_TO_TYPE[kind]
         shape = list(q.shape) + [0] * (4 - q.ndim)
-        data = q.tobytes()
+        data = [memoryview(q).cast("B")]
         n_scales = 0
         if s is not None:
             s = np.ascontiguousarray(s, np.float32)
-            data += s.tobytes()
+            data.append(memoryview(s).cast("B"))
             n_scales = s.size
         hd = struct.pack("<4I2HI", *shape, tt, layer, n_scales)
         _block(out, TENSOR_TYPES[tt][1].format(layer), data, B_TENSOR, _D_OF[q.dtype], 64, hd)
@@ -175,8 +188,6 @@ def write_flm(path, cfg, tensors, vocab=None, version=(1, 0, 0)):
             tensor(kind, l)
     tensor(T_OUT_NORM, 0)
     tensor(T_CLS, 0)
-    with open(path, "wb") as f:
-        f.write(out.bytes())
 
 
 # ------------------------------------------------------------------------------------------------- reader

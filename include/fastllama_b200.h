@@ -80,6 +80,8 @@ typedef struct {
 #define FL_FLAG_NO_PDL     2   /* rows path: plain stream order instead of programmatic dependent launch between its kernels */
 #define FL_FLAG_PROFILE    8   /* persistent kernel records per-CTA time per category (fl_profile_read) */
 #define FL_FLAG_NO_MEGAKERNEL 4 /* run the step as separate kernels (one per phase) instead of the persistent decode kernel */
+#define FL_FLAG_RELAXED    32  /* MEASUREMENT ONLY (7B-shaped INT8 decode): rmsnorm's sum of squares and softmax's sum as tree reductions instead
+                                  of the reference's serial FP32 chains: logits agree to ~1e-3 relative, they are NOT bit-identical */
 #define FL_FLAG_NO_TC      16  /* never use the tensor-core rows path (tcgen05 GEMM): prompts and sequence batches go token by token */
 
 /* ---- lifecycle ---------------------------------------------------------------------------- */
@@ -143,7 +145,7 @@ int   fl_decode_async(fl_engine* e, int seq_slot, int n_steps);
 void* fl_stream(fl_engine* e);
 int   fl_sync(fl_engine* e);
 /* device addresses of per-slot state for zero-copy consumers on the engine stream (e.g. an NCCL all-gather of the
- * sampled token): name in {"token","pos","argmax","out_tokens","logits"}; NULL if unknown. */
+ * sampled token): name in {"token","pos","argmax","out_tokens","logits","gathered"}; NULL if unknown. */
 void* fl_device_ptr(fl_engine* e, const char* name, int seq_slot);
 /* per-CTA SM cycles spent per category by the persistent decode kernel since the last reset:
  * out[cta*32 + k], k = 0 waiting for tagged input words (exchange latency + slowest producer), 1 activation rebuild tail
@@ -164,7 +166,10 @@ int  fl_tap(fl_engine* e, const char* name, float* out, int cap);
 /* ---- multi-GPU (request batch sharded, weights replicated) ---------------------- */
 /* Bind an NCCL communicator created by the host (ncclComm_t passed as void*), or NULL for world == 1. */
 int  fl_set_comm(fl_engine* e, void* nccl_comm, int rank, int world);
-/* all-gather of n_local sampled tokens per rank on the engine stream; no-op copy if world == 1 */
+/* all-gather of n_local sampled tokens per rank (ncclAllGather on the engine stream; a plain copy if world == 1).
+ * local (host, n_local ints) -> all (host, world * n_local ints), synchronous; or local == NULL: gather the tokens just sampled
+ * on the device for slots 0 .. n_local-1 without any host round trip - asynchronous when `all` is NULL too, the result stays
+ * on the device (fl_device_ptr(e, "gathered", 0)). */
 int  fl_allgather_tokens(fl_engine* e, const int32_t* local, int n_local, int32_t* all);
 
 /* ---- per-operator entry points (known-answer / parity tests; host buffers in, host buffers out) -- */

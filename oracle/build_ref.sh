@@ -35,6 +35,13 @@ build "$OUT/libref.so" -march=haswell &
 if grep -qi '^flags.*\<avx512f\>' /proc/cpuinfo; then
     build "$OUT/libref_native.so" -march=native -mavx512f -mavx512bw -mavx512vl -mavx512dq &
 fi
+# The reference-side binding of include/fastllama_b200.h, compiled against the reference's headers (tests/cxx/fl_binding.cpp):
+# reference loader -> fl_upload / fl_forward.  Links nothing of the product: the library is dlopen'ed at run time.
+BIND="$HERE/../tests/cxx/fl_binding.cpp"
+if [ ! "$OUT/libfl_binding.so" -nt "$BIND" ] || [ ! "$OUT/libfl_binding.so" -nt "$HERE/../include/fastllama_b200.h" ]; then
+    echo "g++ -> $OUT/libfl_binding.so"
+    g++ -o "$OUT/libfl_binding.so" $SRCS "$BIND" $COMMON -march=haswell $INCS -lpthread -lm -ldl &
+fi
 wait
 # The reference CLI itself, for the CPU baseline (bench.py --impl reference can also use libref.so).
 if [ ! -x "$OUT/main" ] || [ "$OUT/main" -ot "$HERE/build_ref.sh" ]; then

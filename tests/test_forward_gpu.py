@@ -163,7 +163,9 @@ def test_forward_batch_one_launch_for_all_sequences_matches_oracle(fl, name, spe
             P.port_forward(pm, ptr(t), 1, pr.size + k, ptr(logits))
             seq.append(P.port_argmax(ptr(logits), spec.vocab_size))
         want.append(seq)
-    eng = make_engine(fl, spec, qm, qt, gs, max_seqs=n_seqs)
+    # FLAG_NO_TC: this test pins the multi-sequence variant of the persistent kernel (INT16's only batched path); the tensor-core
+    # rows path INT8 engines use by default is pinned in tests/test_tc_gemm_gpu.py
+    eng = make_engine(fl, spec, qm, qt, gs, max_seqs=n_seqs, flags=fl.FLAG_NO_TC)
     toks = np.array([eng.forward(pr, 0, slot=i, want_logits=False, want_argmax=True) for i, pr in enumerate(prompts)], np.int32)
     pos = np.array([pr.size for pr in prompts], np.int32)
     got = [[int(t)] for t in toks]

@@ -13,11 +13,11 @@ import sys
 import numpy as np
 import pytest
 
-from oracle_libs import port, ptr, bits, PortConfig, Q_INT8, Q_INT16
+from oracle_libs import port, ref, ptr, bits, PortConfig, Q_INT8, Q_INT16
 from fixtures import ModelSpec, LLAMA2_7B, prompt_tokens
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from bench import synth_int8_model  # noqa: E402
+from bench import synth_int8_model, Synth  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
@@ -93,3 +93,96 @@ def test_7b_full_depth_persistent_kernel_equals_phase_kernels_and_is_reproducibl
     assert np.array_equal(bits(again), bits(first))
     for e in engines:
         e.close()
+
+
+def test_7b_width_eight_sequences_one_weight_pass_matches_oracle(fl):
+    """BASELINE configs[3] per GPU at the real widths: 8 sequences advanced together by the tensor-core rows path (one weight
+    pass per step) against the oracle run on every sequence alone (short contexts: the oracle is one CPU thread), and at
+    contexts around 160 against the same engine decoding every sequence alone through the persistent kernel, which the test
+    above pins to the oracle at this width."""
+    spec = WIDTH_CASES[0][1]
+    n_seqs = 8
+    P = port()
+    pc = PortConfig(spec.dim, spec.hidden_dim, spec.n_layers, spec.n_heads, spec.n_kv_heads, spec.head_size, spec.vocab_size, 1024, Q_INT8, 64)
+    pm = P.port_model_create(C.byref(pc))
+    eng = fl.Engine(spec.dim, spec.hidden_dim, spec.n_layers, spec.n_heads, spec.n_kv_heads, spec.vocab_size, max_seq_len=1024, max_seqs=n_seqs)
+    solo = fl.Engine(spec.dim, spec.hidden_dim, spec.n_layers, spec.n_heads, spec.n_kv_heads, spec.vocab_size, max_seq_len=1024, flags=fl.FLAG_NO_TC)
+    for (kind, layer), (q, s) in synth_int8_model(spec, seed=3):
+        q = np.ascontiguousarray(q)
+        s = None if s is None else np.ascontiguousarray(s)
+        rows = q.shape[0] if q.ndim == 2 else 1
+        assert P.port_model_set_tensor(pm, kind, layer, ptr(q), ptr(s) if s is not None else None, rows, q.shape[-1]) == 0
+        eng.upload(kind, layer, q, s)
+        solo.upload(kind, layer, q, s)
+    eng.finalize(); solo.finalize()
+    # ---- short contexts against the oracle
+    prompts = [prompt_tokens(spec, 2 + i % 4, seed=30 + i) for i in range(n_seqs)]
+    n_steps = 3
+    logits = np.empty(spec.vocab_size, np.float32)
+    want = []
+    for pr in prompts:
+        P.port_model_reset(pm)
+        P.port_forward(pm, ptr(pr), pr.size, 0, ptr(logits))
+        seq = [P.port_argmax(ptr(logits), spec.vocab_size)]
+        for k in range(n_steps):
+            P.port_forward(pm, ptr(np.array([seq[-1]], np.int32)), 1, pr.size + k, ptr(logits))
+            seq.append(P.port_argmax(ptr(logits), spec.vocab_size))
+        want.append(seq)
+    toks = np.array([eng.forward(pr, 0, slot=i, want_logits=False, want_argmax=True) for i, pr in enumerate(prompts)], np.int32)
+    pos = np.array([pr.size for pr in prompts], np.int32)
+    got = [[int(t)] for t in toks]
+    for _ in range(n_steps):
+        toks = eng.forward_batch(toks, pos)
+        pos += 1
+        for i, t in enumerate(toks):
+            got[i].append(int(t))
+    assert got == want
+    P.port_model_free(pm)
+    # ---- contexts around 160 (the benchmark's mean): prompt chunks on the tensor cores, then device-resident batched decode
+    prompts = [prompt_tokens(spec, 150 + 3 * i, seed=60 + i) for i in range(n_seqs)]
+    n_new = 12
+    want = [solo.generate_greedy(pr, n_new).tolist() for pr in prompts]
+    for i, pr in enumerate(prompts):
+        eng.forward(pr, 0, slot=i, want_logits=False)
+    eng.decode_batch_async(n_seqs, n_new)
+    for i in range(n_seqs):
+        out = eng.out_tokens(n_new + 1, slot=i).tolist()
+        stop = want[i].index(0) + 1 if 0 in want[i] else len(want[i])
+        assert out[:stop] == want[i][:stop], i
+    eng.close(); solo.close()
+
+
+def test_7b_full_depth_logits_equal_the_real_reference(fl, tmp_path):
+    """Full depth against the REAL reference: the 32-layer 7B INT8 benchmark model is written as an .flm by our writer, loaded by
+    the unmodified reference (oracle/_ref/libref.so: its loader, thread pool, AVX2 kernels) and by the engine; prefill 3 tokens
+    + 4 decode steps must give bit-identical logits.  Needs libref.so (built where /root/reference exists, shipped to the GPU box)."""
+    R = ref()
+    if R is None:
+        pytest.skip("oracle/_ref/libref.so not built")
+    from flm_inputs import config_of, micro_vocab
+    spec = LLAMA2_7B
+    syn = Synth(spec, seed=0)
+    path = str(tmp_path / "bench7b.flm")
+    fl.flm.write_flm(path, config_of(spec, Q_INT8, 64, "bench7b"), syn.get, micro_vocab(spec.vocab_size))
+    h = R.ref_model_load(path.encode(), b"", 1, Q_INT8, os.cpu_count() or 8, 64, 0)
+    assert h
+    os.remove(path)
+    eng = fl.Engine(spec.dim, spec.hidden_dim, spec.n_layers, spec.n_heads, spec.n_kv_heads, spec.vocab_size, max_seq_len=1024)
+    for (kind, layer), (q, s) in syn.items():
+        eng.upload(kind, layer, q, s)
+    eng.finalize()
+    del syn
+    toks = prompt_tokens(spec, 3, seed=1)
+    want = np.empty(spec.vocab_size, np.float32)
+    R.ref_forward(h, ptr(toks), toks.size, 0, ptr(want))
+    got = eng.forward(toks, 0)
+    assert np.array_equal(bits(got), bits(want)), ("prefill", np.abs(got - want).max())
+    pos = toks.size
+    for step in range(4):
+        t = np.array([int(np.argmax(want))], np.int32)
+        R.ref_forward(h, ptr(t), 1, pos, ptr(want))
+        got = eng.forward(t, pos)
+        assert np.array_equal(bits(got), bits(want)), (step, np.abs(got - want).max())
+        pos += 1
+    R.ref_model_free(h)
+    eng.close()
