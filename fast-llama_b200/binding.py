@@ -31,7 +31,8 @@ class FlConfig(C.Structure):
 
 def lib_path():
     # FL_PROF_LIB=1 selects the build with the in-kernel profiling counters compiled in (profiles/*.py set it)
-    name = "libfastllama_b200_prof.so" if os.environ.get("FL_PROF_LIB") == "1" else "libfastllama_b200.so"
+    sel = os.environ.get("FL_PROF_LIB", "")
+    name = "libfastllama_b200.so" if not sel else "libfastllama_b200_prof.so" if sel == "1" else f"libfastllama_b200_{sel}.so"     # A/B builds: csrc/Makefile `variants`
     return os.path.join(HERE, name)
 
 

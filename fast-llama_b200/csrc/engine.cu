@@ -96,7 +96,7 @@ struct fl_engine {
     bool use_mega = false;
     int cph = 1;                        // CTAs per head in the persistent kernel; also the column blocking of the V cache
     MegaLayer* mega_layers = nullptr;
-    uint2 *x1t = nullptr, *qkvt = nullptr, *attnt = nullptr, *hdt = nullptr, *score_t = nullptr;   // tagged exchange buffers (sequence 0)
+    uint2 *x1t = nullptr, *qkvt = nullptr, *attnt = nullptr, *hdt = nullptr, *hdqt = nullptr, *score_t = nullptr;   // tagged exchange buffers (sequence 0)
     uint8_t* xchg = nullptr;          // one block per sequence slot: [x1t | qkvt | attnt | hdt | score_t | am], xchg_stride bytes apart
     size_t xchg_stride = 0;
     uint4* am = nullptr;
@@ -388,12 +388,15 @@ int setup_mega(fl_engine* e) {
         const size_t o_x1 = take((c.dim + 2) * sizeof(uint2)), o_qkv = take((qkv_rows + 2) * sizeof(uint2));
         const size_t o_attn = take((c.dim + 2) * sizeof(uint2)), o_hd = take((c.hidden_dim + 2) * sizeof(uint2));
         const size_t o_sc = take(((size_t)c.n_heads * score_stride + 2) * sizeof(uint2)), o_am = take(sizeof(uint4) * e->n_sms);
+        // quantised hd: hidden * es / 4 payload words, then one scale per group, every word tagged (build_hd)
+        const size_t o_hdq = take(((size_t)c.hidden_dim * es / 4 + c.hidden_dim / gs + 2) * sizeof(uint2));
         e->xchg_stride = off;
         CK(e, cudaMalloc(&e->xchg, off * c.max_seqs));
         CK(e, cudaMemsetAsync(e->xchg, 0, off * c.max_seqs, e->stream));      // tag 0 is never used
         e->x1t = reinterpret_cast<uint2*>(e->xchg + o_x1); e->qkvt = reinterpret_cast<uint2*>(e->xchg + o_qkv);
         e->attnt = reinterpret_cast<uint2*>(e->xchg + o_attn); e->hdt = reinterpret_cast<uint2*>(e->xchg + o_hd);
         e->score_t = reinterpret_cast<uint2*>(e->xchg + o_sc); e->am = reinterpret_cast<uint4*>(e->xchg + o_am);
+        e->hdqt = reinterpret_cast<uint2*>(e->xchg + o_hdq);
     }
     CK(e, cudaMalloc(&e->prof, sizeof(unsigned long long) * 32 * e->n_sms));
     CK(e, cudaMemsetAsync(e->prof, 0, sizeof(unsigned long long) * 32 * e->n_sms, e->stream));
@@ -403,7 +406,7 @@ int setup_mega(fl_engine* e) {
     p.layers = e->mega_layers; p.cls = e->rk_cls.d; p.out_norm = e->out_norm; p.emb = e->emb;
     p.att_norm = e->att_norm; p.ffn_norm = e->ffn_norm;
     p.off_qkv = e->rk_off[RK_QKV]; p.off_wo = e->rk_off[RK_WO]; p.off_w13 = e->rk_off[RK_W13]; p.off_w2 = e->rk_off[RK_W2]; p.off_cls = e->rk_off[RK_CLS];
-    p.x1t = e->x1t; p.qkvt = e->qkvt; p.attnt = e->attnt; p.hdt = e->hdt; p.score_t = e->score_t; p.am = e->am; p.logits = e->logits;
+    p.x1t = e->x1t; p.qkvt = e->qkvt; p.attnt = e->attnt; p.hdt = e->hdt; p.hdqt = e->hdqt; p.score_t = e->score_t; p.am = e->am; p.logits = e->logits;
     p.rope = e->rope; p.out_cap = e->out_cap; p.score_stride = score_stride;
     p.tap_norm = e->tap_norm; p.prof = (c.flags & FL_FLAG_PROFILE) ? e->prof : nullptr;
     p.evlog = (c.flags & FL_FLAG_PROFILE) ? e->evlog : nullptr;
@@ -413,11 +416,9 @@ int setup_mega(fl_engine* e) {
     const int cph = e->cph;
     p.cph = cph;
     const int dw = c.head_size / cph;
-    int v_chunk_bytes = 16384;            // profiles/r01: PV costs ~0.45 us per chunk on top of the chain; 4 KB 178, 8 KB 138, 16 KB 122 us per token
-#ifdef FL_PROFILE                         // tuning knobs exist in the profiling build only (libfastllama_b200_prof.so)
-    if (getenv("FL_VCHUNK")) v_chunk_bytes = atoi(getenv("FL_VCHUNK"));
-#endif
-    p.v_chunk_rows = v_chunk_bytes / 4 / dw;          // V chunks of 16 KB: rows x dims-per-part fp32
+    // V chunks of kVChunkRows rows x dims-per-part fp32 (4 KB at 32 dims): small chunks keep a whole short context in flight
+    // at once (the staging area holds ~10 of them); the PV loop hides the per-chunk cost (profiles/r02)
+    const int v_chunk_bytes = kVChunkRows * dw * 4;
     // shared memory carve-up
     const int kmax = c.dim > c.hidden_dim ? c.dim : c.hidden_dim;
     const int nkc_max = ceil_div(kmax * es, kStageRowBytes);
@@ -425,7 +426,7 @@ int setup_mega(fl_engine* e) {
     auto al = [](size_t v, size_t a) { return (v + a - 1) / a * a; };
     size_t off = 0;
     p.off_misc = (int)off; off += 2048;
-    p.off_att = (int)off; off += al((size_t)c.max_seq_len * 4 + 64, 128);
+    p.off_att = (int)off; off += al((size_t)c.max_seq_len * 4 + 192, 128);      // + one chunk of zero weights past the last position
     p.off_xs = (int)off; off += al((size_t)nkc_max * gps * 4, 128);
     p.off_vbars = (int)off; off += 128;
     p.off_psrc = (int)off; off += al((size_t)(4 * L + 1) * 8, 128);      // this CTA's weight-stream start of every phase
@@ -491,7 +492,7 @@ int launch_mega(fl_engine* e, int slot, int n_steps, int n_seqs = 1) {
     if (slot > 0) {     // the exchange buffers of slot 0 serve a single sequence in any slot; a batch starts at its own block
         const size_t o = n_seqs > 1 ? (size_t)slot * e->xchg_stride : 0;
         auto sh = [&](auto*& ptr) { ptr = reinterpret_cast<std::remove_reference_t<decltype(ptr)>>(reinterpret_cast<uint8_t*>(ptr) + o); };
-        sh(p.x1t); sh(p.qkvt); sh(p.attnt); sh(p.hdt); sh(p.score_t); sh(p.am);
+        sh(p.x1t); sh(p.qkvt); sh(p.attnt); sh(p.hdt); sh(p.hdqt); sh(p.score_t); sh(p.am);
     }
     const uint64_t tags = (uint64_t)n_steps * (uint64_t)(c.n_layers + 1) * kTagsPerLayer;
     if ((uint64_t)e->epoch + tags >= 0xfff00000ull) {
@@ -744,7 +745,11 @@ int fl_create(const fl_config* cfg, int device, fl_engine** out) {
     CKF(cudaGetDeviceProperties(&prop, device));
     e->n_sms = prop.multiProcessorCount;
     CKF(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+#ifdef FL_CPH2
+    e->cph = 2;     // A/B build
+#else
     e->cph = 4;
+#endif
     while (e->cph > 1 && (c.n_heads * e->cph > e->n_sms || c.head_size / e->cph < 16)) e->cph /= 2;
 
     const int L = c.n_layers, kv_dim = c.head_size * c.n_kv_heads;

@@ -53,9 +53,26 @@ namespace fl {
 
 constexpr int kConsumerWarps = 8;
 constexpr int kConsumerThreads = kConsumerWarps * 32;
-constexpr int kMegaThreads = kConsumerThreads + 64;     // + TMA producer warp + chain warp
+#ifdef FL_NO_SETMAXNREG
+constexpr int kMegaThreads = kConsumerThreads + 64;     // A/B build: no register re-division (168 per thread everywhere)
+#else
+constexpr int kMegaThreads = kConsumerThreads + 128;    // + a third warpgroup: TMA producer warp, chain warp, two warps that exit at once
+#endif
+// Registers are re-divided between the warpgroups at kernel start (setmaxnreg): with three warps per scheduler the launch
+// allocation is 168 per thread, which the consumers' phase loop does not fit without spilling (and with ~227 KB of shared
+// memory carved out a spill is an L2 round trip); the producer and chain warps need far less.  3 x 168 = 88 + 2 x 208 per scheduler (with fewer than 88 ptxas serialises the chain warp's load batches).
+constexpr int kRegsService = 88, kRegsConsumer = 208;
+#ifdef FL_CHAIN_W9
+constexpr bool kChainOnChainWarp = true;      // A/B build: the rmsnorm sum-of-squares chain on the chain warp, following the polls (sumsq_service)
+#else
+// measured (profiles/r02/ab_chain_warp.log): 386 tokens/s with the chain on the chain warp against 438 with the chain on consumer
+// warp 7 after the poll - the overlap with the poll's tail does not pay for whatever slows the chain on warp 9
+constexpr bool kChainOnChainWarp = false;
+#endif
+static_assert(kRegsService + 2 * kRegsConsumer <= 3 * 168, "the CTA's register pool is what the launch allocated: 3 warps x 168 per scheduler (a larger sum deadlocks in setmaxnreg.inc)");
 constexpr int kPairGroups = 64;                          // groups (all sub-streams together) per superblock = per pair buffer (16 KB)
 constexpr int kTagsPerLayer = 8;
+constexpr int kVChunkRows = 32;                         // cached V rows per chunk of the attention part's ring (8 quads of 4 positions)
 constexpr int kSerialWarp = kConsumerWarps - 1;   // runs the single-warp serial sections: the scheduler favours the highest warp id of a
                                                   // sub-partition, and warp 7 shares its sub-partition only with warp 3 (not with the producer / chain warps)
 constexpr int kProfThread = kConsumerThreads - 1;  // keeps the profiling clock: last lane of the serial warp (in the PV group, not a chain lane)
@@ -77,6 +94,7 @@ struct MegaParams {
     const float* emb;
     const unsigned long long *off_qkv, *off_wo, *off_w13, *off_w2, *off_cls;   // per-CTA stream offsets inside the packed matrices
     uint2* x1t; uint2* qkvt; uint2* attnt; uint2* hdt;   // tagged activation vectors: word i = (float bits, tag)
+    uint2* hdqt;                      // the QUANTISED hd vector, tagged: per group GS * ES / 4 payload words, then the scale (build_hd)
     uint2* score_t;                   // [n_heads][score_stride] tagged raw scores exchanged between the CTAs of a head
     uint4* am;                        // [gridDim] argmax partials (value bits, tag, index, tag)
     float* logits;
@@ -112,19 +130,20 @@ constexpr int kMaxSeqsPerLaunch = 16;      // per-sequence state lives in 64 spa
 
 // the per-sequence buffers of a launch (MS = false: the single sequence the pointers in MegaParams already describe)
 struct SeqView {
-    uint2 *x1t, *qkvt, *attnt, *hdt, *score_t;
+    uint2 *x1t, *qkvt, *attnt, *hdt, *hdqt, *score_t;
     uint4* am;
     float *kc, *vc;
 };
 template <bool MS>
 __device__ __forceinline__ SeqView seq_view(const MegaParams& p, int s) {
-    SeqView v{p.x1t, p.qkvt, p.attnt, p.hdt, p.score_t, p.am, p.k_cache, p.v_cache};
+    SeqView v{p.x1t, p.qkvt, p.attnt, p.hdt, p.hdqt, p.score_t, p.am, p.k_cache, p.v_cache};
     if (MS) {
         const unsigned long long o = p.xchg_stride * (unsigned long long)s;
         v.x1t = reinterpret_cast<uint2*>(reinterpret_cast<char*>(p.x1t) + o);
         v.qkvt = reinterpret_cast<uint2*>(reinterpret_cast<char*>(p.qkvt) + o);
         v.attnt = reinterpret_cast<uint2*>(reinterpret_cast<char*>(p.attnt) + o);
         v.hdt = reinterpret_cast<uint2*>(reinterpret_cast<char*>(p.hdt) + o);
+        v.hdqt = reinterpret_cast<uint2*>(reinterpret_cast<char*>(p.hdqt) + o);
         v.score_t = reinterpret_cast<uint2*>(reinterpret_cast<char*>(p.score_t) + o);
         v.am = reinterpret_cast<uint4*>(reinterpret_cast<char*>(p.am) + o);
         v.kc = p.k_cache + p.cache_stride * (unsigned long long)s;
@@ -423,155 +442,374 @@ __device__ __forceinline__ float sumsq_chain_t(const float* xt, int n, int lane)
     return res;
 }
 
+// In the persistent kernel the same chain is run by the CHAIN WARP (idle between two drains) while the consumer warps are still polling: consumer warp w
+// stores its share of the transposed vector pass by pass (a pass of a warp = 4 quantisation groups = one SEGMENT of
+// 4 * GS consecutive elements; segments in element order: pass-major, then warp) and publishes (build << 8 | passes stored) in
+// seg_flags[w].  The chain follows that frontier in element order, so it has usually covered most of the vector when the last
+// word of the exchange arrives - instead of starting there.  Result (the rmsnorm scale) -> misc[18], then misc word 19 = build + 1.
+template <int GS>
+__device__ __forceinline__ void sumsq_service(const float* xt, float* misc, int K, uint32_t bseq, int lane) {
+    uint32_t* mw = reinterpret_cast<uint32_t*>(misc);
+    const uint32_t* seg_flags = mw + 416;
+    constexpr int FPG = GS / 16;                            // float4s per chain lane per group
+    const int G = K / GS;
+    const int total = K >> 4;                               // float4s per chain lane
+    const float4* pl = reinterpret_cast<const float4*>(xt + (lane & 3) * (K >> 2));      // lanes 4..31 shadow lanes 0..3 (no divergence)
+    int ready = 0, seg = 0;                                 // float4s known to be stored; next segment to look at
+    // The flag of the next segment is READ at the start of a unit and LOOKED AT after the unit's FMAs, so its latency stays off
+    // the chain; only when the loads of the next unit would pass the frontier does the warp spin.  No fence on this side: the
+    // data loads are issued after the flag value has arrived (the writer fences between its stores and its flag).
+    auto flag_need = [&](int sg) { return (bseq << 8) | (uint32_t)((sg >> 3) + 1); };
+    auto take = [&]() { ready += min(4, G - 4 * seg) * FPG; ++seg; };
+    auto wait_for = [&](int upto) {
+        while (ready < upto) {
+            while ((int)(ld_shared_volatile_u32(seg_flags + (seg & 7)) - flag_need(seg)) < 0) { }
+            take();
+        }
+    };
+    auto fma4 = [](const float4 (&v)[4], float acc) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            acc = __fmaf_rn(v[u].x, v[u].x, acc); acc = __fmaf_rn(v[u].y, v[u].y, acc);
+            acc = __fmaf_rn(v[u].z, v[u].z, acc); acc = __fmaf_rn(v[u].w, v[u].w, acc);
+        }
+        return acc;
+    };
+    float acc = 0.0f;
+    int i = 0;                                              // float4s consumed
+    if (total >= 4) {
+        float4 a[4], b[4];
+        wait_for(total < 8 ? total : 8);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) a[u] = pl[u];
+        int ps = seg;                                       // the segment whose flag `f` was read for
+        uint32_t f = ld_shared_volatile_u32(seg_flags + (seg & 7));
+        // one unit: `cur` holds float4s [i, i + 4) and the next unit's data are known to be stored.  Everything between the
+        // loads and the closing branch is one basic block, so the bookkeeping interleaves with the dependent FMAs.
+        auto step = [&](const float4 (&cur)[4], float4 (&nxt)[4]) {
+            const bool more = i + 8 <= total;
+            if (more) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) nxt[u] = pl[i + 4 + u];
+            }
+            acc = fma4(cur, acc);
+            // the flag read during the previous unit; then read the next one
+            if (ps == seg && 4 * seg < G && (int)(f - flag_need(seg)) >= 0) take();
+            ps = seg;
+            f = ld_shared_volatile_u32(seg_flags + (seg & 7));
+            i += 4;
+            if (more && i + 8 <= total && ready < i + 8) wait_for(i + 8);
+            return more;
+        };
+#pragma unroll 1
+        while (true) {
+            if (!step(a, b)) break;
+            if (!step(b, a)) break;
+        }
+    }
+#pragma unroll 1
+    for (; i < total; ++i) {
+        wait_for(i + 1);
+        const float4 v = pl[i];
+        acc = __fmaf_rn(v.x, v.x, acc); acc = __fmaf_rn(v.y, v.y, acc);
+        acc = __fmaf_rn(v.z, v.z, acc); acc = __fmaf_rn(v.w, v.w, acc);
+    }
+    const float l0 = __shfl_sync(kFull, acc, 0), l1 = __shfl_sync(kFull, acc, 1);
+    const float l2 = __shfl_sync(kFull, acc, 2), l3 = __shfl_sync(kFull, acc, 3);
+    float res = __fadd_rn(0.0f, l0);
+    res = __fadd_rn(res, l1);
+    res = __fadd_rn(res, l2);
+    res = __fadd_rn(res, l3);
+    if (lane == 0) {
+        misc[18] = rms_scale(res, K);
+        __threadfence_block();
+        st_shared_volatile_u32(mw + 19, bseq + 1u);
+    }
+}
+
 // Rebuild the quantised activation vector of a phase in shared memory (every CTA, redundantly) from the tagged vector
-// `src`, waiting for every word to carry `tag`.
+// `src` (K = dim elements: the W2 input goes through build_hd below), waiting for every word to carry `tag`.
 //   gain != NULL: y = (x*w)*r, r = 1/sqrt(mean(x^2)+eps) (simd::rmsnorm, x86_simd.cpp:1754);  gain == NULL: y = x.
-// Thread layout: 8 lanes per quantisation group, 32 groups per pass, MAXP passes per batch; all loads of a batch are in
-// flight before the first tag is looked at.  The rmsnorm case needs the whole vector before its scale is known, so it
-// must fit ONE batch (K <= 24 * 256 = 6144, checked by the host): the products x*w and the group maxima wait in
-// registers while warp 0 walks the sum-of-squares chain (max |(x*w)*r| == (max |x*w|)*r: rounding is monotonic, r > 0).
+// Thread layout: 8 lanes per quantisation group, 32 groups per pass, at most MAXP passes (K <= 24 * 256 = 6144, checked by
+// the host): all loads are in flight before the first tag is looked at, and the values wait in registers.
+// The rmsnorm case validates its words pass by pass and hands them to the chain warp through the transposed vector xt
+// (sumsq_service), so the sum-of-squares chain overlaps the poll; the products x*w and the group maxima are formed meanwhile
+// (max |(x*w)*r| == (max |x*w|)*r: rounding is monotonic, r > 0).
 // RX (FL_FLAG_RELAXED, measurement of what bit-exactness costs): the sum of squares is a tree reduction instead of the
 // reference's four 1024-step FMA chains - same value up to FP32 rounding (~1e-7 relative), NOT the reference's bits.
 template <int QT, int GS, bool RX = false>
 __device__ __forceinline__ void build_activation(uint8_t* xq, float* xs, float* xt, float* misc, const uint2* src, uint32_t tag,
-                                                 const float* gain, int K, float* tap, int tid, Prof& pf, uint32_t* gate = nullptr, uint32_t gate_val = 0u) {
+                                                 const float* gain, int K, float* tap, int tid, Prof& pf, uint32_t* gate, uint32_t gate_val,
+                                                 uint32_t bseq, uint32_t pairs_need) {
     using RK = Rk<QT, GS>;
     constexpr int PER = GS / 8;                 // values per thread per group
     constexpr int LPP = PER / 2;                // 16-byte loads per thread per pass
     constexpr int GPP = kConsumerThreads / 8;   // groups per pass
-    constexpr int MAXP = 24 / PER;              // passes per batch (24 values per thread: registers, not shared memory)
+    constexpr int MAXP = 24 / PER;              // passes (24 values per thread: registers, not shared memory)
     const int warp = tid >> 5, lane = tid & 31;
     const int kpad_bytes = ceil_div(K * RK::ES, kStageRowBytes) * kStageRowBytes;      // the image is padded to whole stages
     const int G = K / GS;
     const int sub = tid & 7, g0 = tid >> 3;
     const int n_pass = ceil_div(G, GPP);
+    uint32_t* mw = reinterpret_cast<uint32_t*>(misc);
+    const bool chain = gain && !RX && kChainOnChainWarp;      // the exact rmsnorm: the chain warp computes the scale
     uint4 w[MAXP][LPP];
-    float4 gw[MAXP][PER / 4];
-    // all loads of a batch are issued before the first tag is looked at; the NEXT batch's loads are issued as soon as this
-    // batch's values have left `w`, so their round trip overlaps this batch's quantisation (hd needs two batches)
-    auto issue_batch = [&](int b0) {
+#pragma unroll
+    for (int ps = 0; ps < MAXP; ++ps) {
+        const int g = g0 + ps * GPP;
+        if (ps < n_pass && g < G) {
+            const uint2* s = src + g * GS + sub * PER;
+#pragma unroll
+            for (int q = 0; q < LPP; ++q) w[ps][q] = ld_tag2(s + 2 * q);
+        }
+    }
+    if (chain) {
+        // xt lies on top of the pair buffers: this CTA's chain warp must have finished the previous drain
+        if (lane == 0) while ((int)(ld_shared_volatile_u32(mw + 29) - pairs_need) < 0) __nanosleep(20);
+        __syncwarp();
+    }
+    // poll: re-issue the stale loads of every pass; a pass whose words are all valid (and whose predecessors are) is handed
+    // to the chain warp at once
+    float y[MAXP][PER];
+    int published = 0;                          // passes of this warp the chain warp may read (warp-uniform)
+    bool again;
+    do {
+        again = false;
 #pragma unroll
         for (int ps = 0; ps < MAXP; ++ps) {
-            const int g = g0 + (b0 + ps) * GPP;
-            if (b0 + ps < n_pass && g < G) {
+            const int g = g0 + ps * GPP;
+            bool ok = true;
+            if (ps < n_pass && g < G) {
                 const uint2* s = src + g * GS + sub * PER;
 #pragma unroll
-                for (int q = 0; q < LPP; ++q) w[ps][q] = ld_tag2(s + 2 * q);
-                if (gain) {
+                for (int q = 0; q < LPP; ++q)
+                    if (w[ps][q].y != tag || w[ps][q].w != tag) { w[ps][q] = ld_tag2(s + 2 * q); ok = false; }
+            }
+            if (!ok) again = true;
+            if (chain && ps < n_pass && published == ps && __all_sync(kFull, ok)) {
+                if (g < G) {
+                    const int e0 = g * GS + sub * PER;                   // multiple of 4
+                    // raw x -> transposed vector for the chain
+                    if constexpr (PER == 8) {
 #pragma unroll
-                    for (int q = 0; q < PER / 4; ++q) gw[ps][q] = __ldg(reinterpret_cast<const float4*>(gain + g * GS + sub * PER) + q);
+                        for (int j = 0; j < 4; ++j)
+                            *reinterpret_cast<float2*>(xt + j * (K >> 2) + (e0 >> 2)) = make_float2(__uint_as_float(j & 1 ? w[ps][j >> 1].z : w[ps][j >> 1].x), __uint_as_float(j & 1 ? w[ps][2 + (j >> 1)].z : w[ps][2 + (j >> 1)].x));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) xt[j * (K >> 2) + (e0 >> 2)] = __uint_as_float(j & 1 ? w[ps][j >> 1].z : w[ps][j >> 1].x);
+                    }
+                }
+                __threadfence_block();
+                __syncwarp();
+                ++published;
+                if (lane == 0) st_shared_volatile_u32(mw + 416 + warp, (bseq << 8) | (uint32_t)published);
+            }
+        }
+        if (chain) again = __any_sync(kFull, again) || published < n_pass;
+#ifndef FL_POLL_NOSLEEP
+        if (again) __nanosleep(100);            // a poll that failed is not worth repeating at once: the LSU is shared with warps still working
+#endif
+    } while (again);
+    pf.stop(tid, 0);
+    pf.log(tid & 31, tid >> 5, 9, 0);
+    pf.mark(tid, pf.trace_slot, pf.trace_slot >= 0);
+    // every warp has left the previous phase (its drain / attention read the image this build overwrites)
+    consumer_sync();
+    // the input is here: the producer may prefetch again (measured: releasing later costs more ring prefetch than it saves in contention)
+    if (gate && tid == 0) st_shared_volatile_u32(gate, gate_val);
+    // zero the padded tail so padded groups contribute fma(0, 0, acc) == acc
+    for (int i = K * RK::ES + tid * 4; i < kpad_bytes; i += kConsumerThreads * 4) *reinterpret_cast<uint32_t*>(xq + i) = 0u;
+    for (int i = G + tid; i < (kpad_bytes / kStageRowBytes) * RK::GPS; i += kConsumerThreads) xs[i] = 0.0f;
+    // values out of the tagged words (the tags' registers are free from here on)
+    float ss_part = 0.0f;
+#pragma unroll
+    for (int ps = 0; ps < MAXP; ++ps) {
+        const int g = g0 + ps * GPP;
+        if (ps < n_pass && g < G) {
+#pragma unroll
+            for (int q = 0; q < LPP; ++q) { y[ps][2 * q] = __uint_as_float(w[ps][q].x); y[ps][2 * q + 1] = __uint_as_float(w[ps][q].z); }
+            if (gain && RX) {
+#pragma unroll
+                for (int i = 0; i < PER; ++i) ss_part = __fmaf_rn(y[ps][i], y[ps][i], ss_part);
+            }
+            if (gain && !RX && !kChainOnChainWarp) {
+                // raw x -> transposed vector for the chain on the serial warp
+                const int e0 = g * GS + sub * PER;                   // multiple of 4
+                if constexpr (PER == 8) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) *reinterpret_cast<float2*>(xt + j * (K >> 2) + (e0 >> 2)) = make_float2(y[ps][j], y[ps][4 + j]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) xt[j * (K >> 2) + (e0 >> 2)] = y[ps][j];
                 }
             }
         }
-    };
-    issue_batch(0);
+    }
+    // the gain vector (16 KB per layer, L2-resident: every CTA reads it) is fetched only now: next to the 12 in-flight 16-byte
+    // loads of the poll it did not fit the register file, and its latency hides behind the sum-of-squares chain
+    float4 gw[MAXP][PER / 4];
+    if (gain) {
+#pragma unroll
+        for (int ps = 0; ps < MAXP; ++ps) {
+            const int g = min(g0 + ps * GPP, G - 1);        // clamped: always a valid address, unused where the thread has no group
+#pragma unroll
+            for (int q = 0; q < PER / 4; ++q) gw[ps][q] = __ldg(reinterpret_cast<const float4*>(gain + g * GS + sub * PER) + q);
+        }
+    }
+    pf.stop(tid, 8);
+    float rr = 1.0f;
+    if (gain && RX) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ss_part = __fadd_rn(ss_part, __shfl_xor_sync(kFull, ss_part, o));
+        if (lane == 0) misc[8 + warp] = ss_part;
+        consumer_sync();
+        float ss = misc[8];
+#pragma unroll
+        for (int w8 = 1; w8 < kConsumerWarps; ++w8) ss = __fadd_rn(ss, misc[8 + w8]);
+        rr = rms_scale(ss, K);
+    } else if (gain && !kChainOnChainWarp) {
+        consumer_sync();
+        if (warp == kSerialWarp) {
+            const float ss = sumsq_chain_t(xt, K, lane);
+            if (lane == 0) misc[18] = rms_scale(ss, K);
+        }
+        consumer_sync();
+        rr = misc[18];
+    } else if (gain) {
+        // the scale from the chain warp
+        if (lane == 0) while (ld_shared_volatile_u32(mw + 19) != bseq + 1u) { }
+        __syncwarp();
+        __threadfence_block();
+        rr = misc[18];
+    }
+    pf.stop(tid, 9);
+#pragma unroll
+    for (int ps = 0; ps < MAXP; ++ps) {
+        const int g = g0 + ps * GPP;
+        float mm = 0.0f;
+        const bool act = ps < n_pass && g < G;
+        if (act) {
+            if (gain) {
+#pragma unroll
+                for (int q = 0; q < PER / 4; ++q) {                 // x*w, multiply_avx256 x86_simd.cpp:1359
+                    y[ps][4 * q] = __fmul_rn(y[ps][4 * q], gw[ps][q].x); y[ps][4 * q + 1] = __fmul_rn(y[ps][4 * q + 1], gw[ps][q].y);
+                    y[ps][4 * q + 2] = __fmul_rn(y[ps][4 * q + 2], gw[ps][q].z); y[ps][4 * q + 3] = __fmul_rn(y[ps][4 * q + 3], gw[ps][q].w);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < PER; ++i) mm = fmaxf(mm, fabsf(y[ps][i]));
+        }
+        float m = group_max8(mm);
+        if (act) {
+            if (gain) {
+#pragma unroll
+                for (int i = 0; i < PER; ++i) y[ps][i] = __fmul_rn(y[ps][i], rr);     // (x*w)*r
+                m = __fmul_rn(m, rr);                               // max |(x*w)*r| == (max |x*w|)*r: rounding is monotonic, r > 0
+            }
+            quant_store<QT, GS>(xq, xs, y[ps], m, g, sub, tap);
+        }
+    }
+    consumer_sync();
+}
+
+// The W2 input (hd, K = hidden) is the one exchange whose size hurts: as tagged fp32 words it is 8 bytes per element read by
+// every CTA (88 KB per CTA, 13 MB through the L2 per layer at the 7B shape, ~2 us of L2 bandwidth alone) followed by the longest
+// quantisation tail.  It needs no vector-wide quantity (no rmsnorm), so it is quantised ONCE: CTA c is the designated quantiser
+// of groups [G c / n, G (c + 1) / n) - it polls their raw words (published by the one or two CTAs that own those W1/W3 rows),
+// quantises them exactly as quant::quantize does (quant_operators.cpp:26-47) and publishes payload words and scale as tagged
+// words; every CTA then polls the quantised vector (K * ES / 4 payload words, then G scales: 23 KB instead of 88 KB) straight
+// into its shared-memory image.  One more L2 hop, a quarter of the bytes and the whole quantisation tail less.
+template <int QT, int GS>
+__device__ __forceinline__ void build_hd(uint8_t* xq, float* xs, const uint2* raw, uint2* qt, uint32_t tag_raw, uint32_t tag_q, int K,
+                                         int tid, Prof& pf, uint32_t* gate, uint32_t gate_val) {
+    using RK = Rk<QT, GS>;
+    constexpr int PER = GS / 8;                             // values per thread of a quantiser group (8 lanes per group)
+    constexpr int EPW = (QT == Q_INT8) ? 4 : 2;             // elements per payload word
+    constexpr int PW = GS / EPW;                            // payload words per group
+    const int G = K / GS;
+    const int NPW = G * PW;                                 // payload words of the vector (even)
+    const int sub = tid & 7;
+    // ---- A: quantise my groups
+    const int g_lo = (int)((long long)G * blockIdx.x / gridDim.x), g_hi = (int)((long long)G * (blockIdx.x + 1) / gridDim.x);
+    const unsigned gmask = 0xffu << (tid & 24);             // the 8 lanes of a group stay together
 #pragma unroll 1
-    for (int b0 = 0; b0 < n_pass; b0 += MAXP) {
+    for (int g = g_lo + (tid >> 3); g < g_hi; g += kConsumerThreads / 8) {
+        const uint2* s = raw + g * GS + sub * PER;
+        uint4 w[PER / 2];
+#pragma unroll
+        for (int q = 0; q < PER / 2; ++q) w[q] = ld_tag2(s + 2 * q);
         bool again;
         do {
             again = false;
 #pragma unroll
-            for (int ps = 0; ps < MAXP; ++ps) {
-                const int g = g0 + (b0 + ps) * GPP;
-                if (b0 + ps < n_pass && g < G) {
-                    const uint2* s = src + g * GS + sub * PER;
+            for (int q = 0; q < PER / 2; ++q)
+                if (w[q].y != tag_raw || w[q].w != tag_raw) { w[q] = ld_tag2(s + 2 * q); again = true; }
+        } while (__any_sync(gmask, again));
+        float y[PER];
+        float m = 0.0f;
 #pragma unroll
-                    for (int q = 0; q < LPP; ++q)
-                        if (w[ps][q].y != tag || w[ps][q].w != tag) { w[ps][q] = ld_tag2(s + 2 * q); again = true; }
-                }
+        for (int q = 0; q < PER / 2; ++q) { y[2 * q] = __uint_as_float(w[q].x); y[2 * q + 1] = __uint_as_float(w[q].z); }
+#pragma unroll
+        for (int i = 0; i < PER; ++i) m = fmaxf(m, fabsf(y[i]));
+        m = fmaxf(m, __shfl_xor_sync(gmask, m, 1));
+        m = fmaxf(m, __shfl_xor_sync(gmask, m, 2));
+        m = fmaxf(m, __shfl_xor_sync(gmask, m, 4));
+        const float sc = __fdiv_rn(m, (QT == Q_INT8) ? 127.0f : 5792.0f);
+        if (sub == 0) st_tag(qt + NPW + g, sc, tag_q);
+        uint32_t pk[PER / EPW];
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            const uint32_t q = (uint32_t)cvtt_x86(__fdiv_rn(y[i], sc)) & ((QT == Q_INT8) ? 0xffu : 0xffffu);
+            pk[i / EPW] = (i % EPW == 0) ? q : (pk[i / EPW] | (q << ((32 / EPW) * (i % EPW))));
+        }
+#pragma unroll
+        for (int i = 0; i < PER / EPW; ++i) st_tag(qt + (size_t)g * PW + sub * (PER / EPW) + i, __uint_as_float(pk[i]), tag_q);
+    }
+#ifdef FL_HD_GATE_EARLY
+    // A/B build: this CTA's share of the quantisation is out; let the producer refill the ring during the second hop
+    if (gate) { consumer_sync(); if (tid == 0) st_shared_volatile_u32(gate, gate_val); }
+#endif
+    // ---- B: the quantised vector -> shared-memory image.  Word pair i of [payload | scales] lands at word pair i of
+    //      [xq | xs] (xs directly behind the payload in index space only: two arrays, one branch).
+    const int NP = (NPW + G + 1) >> 1;                      // 16-byte pairs ([NPW payload words][G scale words], the buffer is padded to a pair)
+    constexpr int MAXL = 6;                                 // loads per thread per batch (7B: 1462 pairs = 5.7 per thread)
+    const int kpad_bytes = ceil_div(K * RK::ES, kStageRowBytes) * kStageRowBytes;
+    uint32_t* xq32 = reinterpret_cast<uint32_t*>(xq);
+    bool first = true;
+#pragma unroll 1
+    for (int base = 0; base < NP; base += MAXL * kConsumerThreads) {
+        uint4 w[MAXL];
+#pragma unroll
+        for (int l = 0; l < MAXL; ++l) {
+            const int pi = base + l * kConsumerThreads + tid;
+            if (pi < NP) w[l] = ld_tag2(qt + 2 * pi);
+        }
+        bool again;
+        do {
+            again = false;
+#pragma unroll
+            for (int l = 0; l < MAXL; ++l) {
+                const int pi = base + l * kConsumerThreads + tid;
+                if (pi < NP && (w[l].y != tag_q || (2 * pi + 1 < NPW + G && w[l].w != tag_q))) { w[l] = ld_tag2(qt + 2 * pi); again = true; }
             }
-            if (again) __nanosleep(100);        // a poll that failed is not worth repeating at once: the LSU is shared with warps still working
+#ifndef FL_POLL_NOSLEEP
+            if (again) __nanosleep(100);
+#endif
         } while (again);
-        pf.stop(tid, 0);
-        pf.log(tid & 31, tid >> 5, 9, b0);
-        if (b0 + MAXP >= n_pass) pf.mark(tid, pf.trace_slot, pf.trace_slot >= 0);
-        if (b0 == 0) {
-            // every warp has left the previous phase (its drain / attention read the image this build overwrites)
-            consumer_sync();
-            // the input is here: the producer may prefetch again (measured: releasing later - after the chain, or after the
-            // second batch of the hd poll - costs more ring prefetch than it saves in contention)
+        if (first) {
+            pf.stop(tid, 0);
+            pf.mark(tid, pf.trace_slot, pf.trace_slot >= 0 && base + MAXL * kConsumerThreads >= NP);
+            consumer_sync();            // every warp has left the previous phase (its drain read the image this build overwrites)
             if (gate && tid == 0) st_shared_volatile_u32(gate, gate_val);
-            // zero the padded tail so padded groups contribute fma(0, 0, acc) == acc
             for (int i = K * RK::ES + tid * 4; i < kpad_bytes; i += kConsumerThreads * 4) *reinterpret_cast<uint32_t*>(xq + i) = 0u;
             for (int i = G + tid; i < (kpad_bytes / kStageRowBytes) * RK::GPS; i += kConsumerThreads) xs[i] = 0.0f;
-        }
-        float y[MAXP][PER];
-        float m[MAXP];
-#pragma unroll
-        for (int ps = 0; ps < MAXP; ++ps) {
-#pragma unroll
-            for (int q = 0; q < LPP; ++q) { y[ps][2 * q] = __uint_as_float(w[ps][q].x); y[ps][2 * q + 1] = __uint_as_float(w[ps][q].z); }
-        }
-        if (!gain && b0 + MAXP < n_pass) issue_batch(b0 + MAXP);
-        float rr = 1.0f;
-        float ss_part = 0.0f;
-        if (gain) {
-            // raw x -> transposed image for the chain; products and group maxima stay in registers
-#pragma unroll
-            for (int ps = 0; ps < MAXP; ++ps) {
-                const int g = g0 + (b0 + ps) * GPP;
-                if (b0 + ps < n_pass && g < G) {
-                    const int e0 = g * GS + sub * PER;                   // multiple of 4
-                    if (RX) {
-#pragma unroll
-                        for (int i = 0; i < PER; ++i) ss_part = __fmaf_rn(y[ps][i], y[ps][i], ss_part);
-                    } else if (PER == 8) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) *reinterpret_cast<float2*>(xt + j * (K >> 2) + (e0 >> 2)) = make_float2(y[ps][j], y[ps][(4 + j) % PER]);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) xt[j * (K >> 2) + (e0 >> 2)] = y[ps][j];
-                    }
-#pragma unroll
-                    for (int q = 0; q < PER / 4; ++q) {                 // x*w, multiply_avx256 x86_simd.cpp:1359
-                        y[ps][4 * q] = __fmul_rn(y[ps][4 * q], gw[ps][q].x); y[ps][4 * q + 1] = __fmul_rn(y[ps][4 * q + 1], gw[ps][q].y);
-                        y[ps][4 * q + 2] = __fmul_rn(y[ps][4 * q + 2], gw[ps][q].z); y[ps][4 * q + 3] = __fmul_rn(y[ps][4 * q + 3], gw[ps][q].w);
-                    }
-                }
-            }
+            first = false;
         }
 #pragma unroll
-        for (int ps = 0; ps < MAXP; ++ps) {
-            const int g = g0 + (b0 + ps) * GPP;
-            float mm = 0.0f;
-            if (b0 + ps < n_pass && g < G) {
-#pragma unroll
-                for (int i = 0; i < PER; ++i) mm = fmaxf(mm, fabsf(y[ps][i]));
-            }
-            m[ps] = group_max8(mm);
-        }
-        if (gain && RX) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) ss_part = __fadd_rn(ss_part, __shfl_xor_sync(kFull, ss_part, o));
-            if (lane == 0) misc[8 + warp] = ss_part;
-            consumer_sync();
-            float ss = misc[8];
-#pragma unroll
-            for (int w = 1; w < kConsumerWarps; ++w) ss = __fadd_rn(ss, misc[8 + w]);
-            rr = rms_scale(ss, K);
-            pf.stop(tid, 9);
-        } else if (gain) {
-            consumer_sync();
-            pf.stop(tid, 8);
-            if (warp == kSerialWarp) {
-                const float ss = sumsq_chain_t(xt, K, lane);
-                if (lane == 0) misc[0] = rms_scale(ss, K);
-            }
-            consumer_sync();
-            pf.stop(tid, 9);
-            rr = misc[0];
-        }
-#pragma unroll
-        for (int ps = 0; ps < MAXP; ++ps) {
-            const int g = g0 + (b0 + ps) * GPP;
-            if (b0 + ps < n_pass && g < G) {
-                if (gain) {
-#pragma unroll
-                    for (int i = 0; i < PER; ++i) y[ps][i] = __fmul_rn(y[ps][i], rr);     // (x*w)*r
-                    m[ps] = __fmul_rn(m[ps], rr);
-                }
-                quant_store<QT, GS>(xq, xs, y[ps], m[ps], g, sub, tap);
-            }
+        for (int l = 0; l < MAXL; ++l) {
+            const int wi = 2 * (base + l * kConsumerThreads + tid);
+            if (wi < NPW) { xq32[wi] = w[l].x; xq32[wi + 1] = w[l].z; }      // NPW is even: a pair never straddles the two arrays
+            else if (wi < NPW + G) { xs[wi - NPW] = __uint_as_float(w[l].x); if (wi + 1 < NPW + G) xs[wi + 1 - NPW] = __uint_as_float(w[l].z); }
         }
     }
     consumer_sync();
@@ -604,59 +842,10 @@ __device__ __forceinline__ void stage_pairs(const uint8_t* sp, int R, const uint
 // the keys, score exchange through L2 (tagged words), full softmax (redundantly per part), PV chains for HS/cph head dims.
 //
 // Everything that does not depend on the new token is requested BEFORE the q/k/v rows are polled: the part's K rows
-// (registers), its V column block (TMA bulk copies into a ring of 16 KB chunks, the V cache is stored in column blocks of
-// HS/cph for exactly this) and the RoPE table row.  The two serial sections - softmax's sum and the PV chains - run
-// as register-double-buffered FP32 chains at ~5.5 cycles per dependent step.
+// (registers), its V column block (TMA bulk copies into a ring of 32-row chunks, the V cache is stored in column blocks of
+// HS/cph for exactly this; up to ~10 chunks = 320 rows are in flight at once) and the RoPE table row.  The two serial
+// sections - softmax's sum and the PV chains - run as register-staged FP32 chains.
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-// rows [i, rows) of one V chunk for one head dim: o = fma(V[t], w_t, o) where |w_t| > 1e-15 (weighted_sum, tf_operators.cpp:325-350).
-// The chain runs on ONE warp, and a B200 sub-partition issues a warp's FP32/INT/LDS instruction every 2+ cycles, so the
-// instructions per row are what it costs (profiles/micro/pv_bench.cu: 14 cycles per row with one LDS per row).  Hence the V
-// cache keeps 4 consecutive positions of a head dim adjacent ([t/4][DW][4]): one LDS.128 brings 4 rows, the loads of the
-// next 16 rows are issued before the current 16 dependent FMAs, and blocks of 16 rows whose weights all pass the threshold
-// (slow == 0: virtually always) take an FFMA-only path.  vb points at this thread's dim inside the chunk: row r is vb[(r/4)*DW*4 + r%4].
-__device__ __forceinline__ float pv_rows(const float* vb, const float* wp, int DW, int i, int rows, uint32_t slow, float o) {
-    auto one = [&](int r) { const float w = wp[r]; if (fabsf(w) > 1e-15f) o = __fmaf_rn(vb[(r >> 2) * (DW * 4) + (r & 3)], w, o); };
-    for (; i < rows && (i & 15); ++i) one(i);
-    if (i + 16 <= rows) {
-        // two register sets: the loads of one 16-row block are in flight while the other block's 16 dependent FMAs run
-        float4 va[4], wa[4], vc[4], wc[4];
-        auto load = [&](float4 (&v)[4], float4 (&w)[4], int r) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) { v[u] = *reinterpret_cast<const float4*>(vb + ((r >> 2) + u) * (DW * 4)); w[u] = *reinterpret_cast<const float4*>(wp + r + 4 * u); }
-        };
-        auto chain = [&](const float4 (&v)[4], const float4 (&w)[4], int r) {
-            if (!((slow >> (r >> 4)) & 1u)) {
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    o = __fmaf_rn(v[u].x, w[u].x, o); o = __fmaf_rn(v[u].y, w[u].y, o);
-                    o = __fmaf_rn(v[u].z, w[u].z, o); o = __fmaf_rn(v[u].w, w[u].w, o);
-                }
-            } else {
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (fabsf(w[u].x) > 1e-15f) o = __fmaf_rn(v[u].x, w[u].x, o);
-                    if (fabsf(w[u].y) > 1e-15f) o = __fmaf_rn(v[u].y, w[u].y, o);
-                    if (fabsf(w[u].z) > 1e-15f) o = __fmaf_rn(v[u].z, w[u].z, o);
-                    if (fabsf(w[u].w) > 1e-15f) o = __fmaf_rn(v[u].w, w[u].w, o);
-                }
-            }
-        };
-        load(va, wa, i);
-#pragma unroll 1
-        while (i + 32 <= rows) {
-            load(vc, wc, i + 16);
-            chain(va, wa, i);
-            load(va, wa, (i + 48 <= rows) ? i + 32 : i + 16);
-            chain(vc, wc, i + 16);
-            i += 32;
-        }
-        if (i + 16 <= rows) { chain(va, wa, i); i += 16; }
-    }
-#pragma unroll 1
-    for (; i < rows; ++i) one(i);
-    return o;
-}
 
 template <int HS, bool RX = false>
 __device__ __forceinline__ void attention_part(const MegaParams& p, const SeqView sv, uint8_t* smem, int layer, int qh, int part, int pos, int bs,
@@ -671,10 +860,10 @@ __device__ __forceinline__ void attention_part(const MegaParams& p, const SeqVie
     float* v_s = k_s + HS;
     float* red = reinterpret_cast<float*>(smem + p.off_misc);
     uint32_t* vcount = reinterpret_cast<uint32_t*>(smem + p.off_misc) + 28;      // V chunks streamed so far by this CTA (ring position)
-    uint32_t* slowbits = reinterpret_cast<uint32_t*>(smem + p.off_misc) + 416;   // bit b of word w: 16-row block 32w + b holds a weight <= 1e-15
     float* v_stage = reinterpret_cast<float*>(smem + p.off_vstage);
     uint64_t* vfull = reinterpret_cast<uint64_t*>(smem + p.off_vbars);
-    const int VR = p.v_chunk_rows, NCH = p.n_vchunks;
+    constexpr int VR = kVChunkRows;
+    const int NCH = p.n_vchunks;
 
     const int hgs = p.n_heads / p.n_kv_heads;
     const int kvh = qh / hgs, g = qh % hgs;
@@ -696,7 +885,6 @@ __device__ __forceinline__ void attention_part(const MegaParams& p, const SeqVie
         mbar_arrive_expect_tx(&vfull[slot], bytes);
         bulk_g2s(v_stage + (size_t)slot * VR * DW, vc + (size_t)c * VR * DW, bytes, &vfull[slot]);
     };
-    if (tid < 32) slowbits[tid] = 0u;
     // K/V rows of earlier tokens were appended by plain stores of another CTA (part 0 of this head); that CTA's chain warp
     // fenced them before it published tagged rows this CTA has polled since (see the Wo epilogue).  Acquire side of that
     // hand-off, before the cache is read through ld.cg (K) and through the async proxy (V bulk copies):
@@ -772,6 +960,7 @@ __device__ __forceinline__ void attention_part(const MegaParams& p, const SeqVie
 
     // ---- scores for this part's keys: float dot_product_avx256 (x86_simd.cpp:1447-1468): 8 FMA chains, then 0 + l0 + ... + l7
     uint2* att_g = sv.score_t + (size_t)qh * p.score_stride;
+    float mloc = -INFINITY;                        // running maximum of the scores this thread stores (softmax's max, fused)
     {
         const float* qj = q_s + j;                 // q values of this AVX lane are re-read from shared memory (registers are scarce)
 #pragma unroll 1
@@ -798,6 +987,7 @@ __device__ __forceinline__ void attention_part(const MegaParams& p, const SeqVie
                 if (j == 0 && t < te) {
                     const float sc = __fmul_rn(tot, p.attn_scale);      // att.multiply(attn_scale), transformer.cpp:443
                     att[t] = sc;
+                    mloc = fmaxf(mloc, sc);
                     if (cph > 1) st_tag(att_g + t, sc, tag_score);
                 }
             }
@@ -813,30 +1003,27 @@ __device__ __forceinline__ void attention_part(const MegaParams& p, const SeqVie
             if (need0 || need1) {
                 uint4 w = ld_tag2(att_g + t);
                 while ((need0 && w.y != tag_score) || (need1 && w.w != tag_score)) w = ld_tag2(att_g + t);
-                if (need0) att[t] = __uint_as_float(w.x);
-                if (need1) att[t + 1] = __uint_as_float(w.z);
+                if (need0) { att[t] = __uint_as_float(w.x); mloc = fmaxf(mloc, __uint_as_float(w.x)); }
+                if (need1) { att[t + 1] = __uint_as_float(w.z); mloc = fmaxf(mloc, __uint_as_float(w.z)); }
             }
         }
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mloc = fmaxf(mloc, __shfl_xor_sync(kFull, mloc, o));
+    if (lane == 0) red[warp] = mloc;
     consumer_sync();
     if (gate && tid == 0) st_shared_volatile_u32(gate, gate_val);       // q / k / v and the scores are in: Wo's prefetch may start (softmax and PV give it time)
     pf.stop(tid, 12);
     pf.log(lane, warp, 13, 0);
 
-    // ---- softmax_sisd (tf_operators.cpp:176-186): max, expf(x - max), serial sum, divide
-    float m = -INFINITY;
-#pragma unroll 1
-    for (int t = tid; t < n; t += kConsumerThreads) m = fmaxf(m, att[t]);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(kFull, m, o));
-    if (lane == 0) red[warp] = m;
-    consumer_sync();
-    m = red[0];
+    // ---- softmax_sisd (tf_operators.cpp:176-186): max (every score passed through exactly one thread's mloc above),
+    //      expf(x - max), serial sum, divide
+    float m = red[0];
 #pragma unroll
     for (int w = 1; w < kConsumerWarps; ++w) m = fmaxf(m, red[w]);
 #pragma unroll 1
     for (int t = tid; t < n; t += kConsumerThreads) att[t] = expf_exact(__fsub_rn(att[t], m));
-    if (tid < 8) att[n + tid] = 0.0f;                      // the chains below read whole float4s
+    if (tid < 32) att[n + tid] = 0.0f;                     // the chains below read whole float4s / whole 32-row chunks of weights
     consumer_sync();
     if (RX) {
         // relaxed: per-thread partial sums, warp tree, 8 partials in order (not the reference's serial order)
@@ -876,8 +1063,9 @@ __device__ __forceinline__ void attention_part(const MegaParams& p, const SeqVie
 #pragma unroll 1
     for (int t = tid; t < n; t += kConsumerThreads) {
         const float w = __fdiv_rn(att[t], sum);
-        att[t] = w;
-        if (!(fabsf(w) > 1e-15f)) atomicOr(slowbits + (t >> 9), 1u << ((t >> 4) & 31));
+        // the new token's weight goes aside (its V row is not in the staged cache): every weight from `pos` to the end of the
+        // last chunk reads 0 and is skipped by the threshold test below
+        if (t == pos) { red[17] = w; att[t] = 0.0f; } else att[t] = w;
     }
     consumer_sync();
     pf.stop(tid, 13);
@@ -885,36 +1073,56 @@ __device__ __forceinline__ void attention_part(const MegaParams& p, const SeqVie
 
     // ---- weighted_sum (tf_operators.cpp:325-350): o = V[0]*w0; t >= 1: if |w_t| > 1e-15: o = fma(V[t], w_t, o) — one chain
     // per head dim, run by the PV group without CTA-wide synchronisation; its first thread refills the chunk ring.
+    // The chain is one warp per 32 head dims and a dependent FMA issues every 4 cycles, so everything else must stay out
+    // of its way: chunks are 32 rows = 8 quads of 4 positions ([t/4][DW][4] layout: one LDS.128 brings 4 rows of a dim, one
+    // broadcast LDS.128 their 4 weights), the quads of chunk c+1 are loaded into the registers chunk c's quads just left,
+    // and every row takes the same predicated FMA (rows from `pos` on carry weight 0; row 0, which the reference multiplies
+    // unconditionally, is taken out of quad 0 before the loop).
     if (pvt >= 0) {
-        long long ck = clock64(), c_wait = 0, c_loop = 0, c_rest = 0;      // cycle split of the PV section (profiling)
         float o = 0.0f;
-        uint32_t slot = vbase % (uint32_t)NCH, par = (vbase / (uint32_t)NCH) & 1u;
-        const float* wp = att;
-#pragma unroll 1
-        for (int c = 0; c < n_chunks; ++c) {
-            { const long long t = clock64(); c_rest += t - ck; ck = t; }
+        if (n_chunks > 0) {
+            uint32_t slot = vbase % (uint32_t)NCH, par = (vbase / (uint32_t)NCH) & 1u;
+            const int qstride = DW * 4;                     // floats between two quads of one head dim
+            float4 va[8], wa[8];
             mbar_wait(&vfull[slot], par);
-            { const long long t = clock64(); c_wait += t - ck; ck = t; }
-            const float* vb = v_stage + (size_t)slot * VR * DW + pvt * 4;
-            const int rows = min(VR, pos - c * VR);
-            const uint32_t slow = (slowbits[(c * VR) >> 9] >> (((c * VR) >> 4) & 31));        // VR <= 64 rows: at most 4 blocks, inside one word
-            int i = 0;
-            if (c == 0) { o = __fmul_rn(vb[0], wp[0]); i = 1; }          // row 0 of my dim
-            o = pv_rows(vb, wp, DW, i, rows, slow, o);
-            wp += VR;
-            { const long long t = clock64(); c_loop += t - ck; ck = t; }
-            // the chunk is consumed: refill its slot with chunk c + NCH
-            if (DW > 32) asm volatile("bar.sync 2, %0;" :: "r"(DW) : "memory"); else __syncwarp(DW == 32 ? kFull : (kFull << (32 - DW)));      // the PV group is the top DW lanes of its warp
-            if (pvt == 0 && c + NCH < n_chunks) issue_v(c + NCH);      // the slot's reads have retired (their values fed the chain)
-            if (++slot == (uint32_t)NCH) { slot = 0; par ^= 1u; }
+            pf.stop(tid, 14);                               // waiting for the first V chunk
+            {
+                const float* vs = v_stage + (size_t)slot * VR * DW + pvt * 4;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { va[u] = *reinterpret_cast<const float4*>(vs + u * qstride); wa[u] = *reinterpret_cast<const float4*>(att + 4 * u); }
+            }
+            o = __fmul_rn(va[0].x, wa[0].x);
+            wa[0].x = 0.0f;
+#pragma unroll 1
+            for (int c = 0; c < n_chunks; ++c) {
+                const bool more = c + 1 < n_chunks;
+                uint32_t nslot = slot + 1u, npar = par;
+                if (nslot == (uint32_t)NCH) { nslot = 0u; npar ^= 1u; }
+                const float* vs = v_stage + (size_t)nslot * VR * DW + pvt * 4;
+                const float* ws = att + (c + 1) * VR;
+                if (more) mbar_wait(&vfull[nslot], npar);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    if (fabsf(wa[u].x) > 1e-15f) o = __fmaf_rn(va[u].x, wa[u].x, o);
+                    if (fabsf(wa[u].y) > 1e-15f) o = __fmaf_rn(va[u].y, wa[u].y, o);
+                    if (fabsf(wa[u].z) > 1e-15f) o = __fmaf_rn(va[u].z, wa[u].z, o);
+                    if (fabsf(wa[u].w) > 1e-15f) o = __fmaf_rn(va[u].w, wa[u].w, o);
+                    if (more) { va[u] = *reinterpret_cast<const float4*>(vs + u * qstride); wa[u] = *reinterpret_cast<const float4*>(ws + 4 * u); }
+                }
+                if (c + NCH < n_chunks) {
+                    // chunk c has been consumed by every thread of the group: refill its slot with chunk c + NCH
+                    if (DW > 32) asm volatile("bar.sync 2, %0;" :: "r"(DW) : "memory"); else __syncwarp(DW == 32 ? kFull : (kFull << (32 - DW)));      // the PV group is the top DW lanes of its warp
+                    if (pvt == 0) issue_v(c + NCH);
+                }
+                slot = nslot; par = npar;
+            }
         }
         {   // the new token's row
-            const float w = att[pos], v = v_s[d0 + pvt];
+            const float w = red[17], v = v_s[d0 + pvt];
             if (n_chunks == 0) o = __fmul_rn(v, w);
             else if (fabsf(w) > 1e-15f) o = __fmaf_rn(v, w, o);
         }
         st_tag(sv.attnt + (size_t)qh * HS + d0 + pvt, o, tag_out);
-        (void)c_wait; (void)c_loop; (void)c_rest;
         if (pvt == 0) {
             *vcount = vbase + (uint32_t)n_chunks;
 #ifdef FL_PROFILE
@@ -950,6 +1158,8 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
         reinterpret_cast<uint32_t*>(smem + p.off_misc)[31] = 0u;
         reinterpret_cast<uint32_t*>(smem + p.off_misc)[29] = 0u;      // phases the chain warp has finished
         reinterpret_cast<uint32_t*>(smem + p.off_misc)[20] = 0u;      // prefetch gate: phases (counted over all steps) the producer may stream
+        reinterpret_cast<uint32_t*>(smem + p.off_misc)[19] = 0u;      // rmsnorm rebuilds whose scale the chain warp has delivered
+        for (int i = 0; i < kConsumerWarps; ++i) reinterpret_cast<uint32_t*>(smem + p.off_misc)[416 + i] = 0u;      // per-warp (rebuild << 8 | passes stored)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     const int n_phases = 4 * p.n_layers + 1;
@@ -960,6 +1170,12 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
     }
     const int* geom = reinterpret_cast<const int*>(smem + p.off_geom);
     __syncthreads();
+#ifndef FL_NO_SETMAXNREG
+    if (warp >= kConsumerWarps) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(kRegsService));
+        if (warp >= kConsumerWarps + 2) return;
+    }
+#endif
 
     if (warp == kConsumerWarps) {
         // ================= TMA producer =================
@@ -1028,6 +1244,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
         // Follows the consumers' schedule superblock by superblock; lane i owns row i of the current tile.
         uint32_t sbseq = 0;                                  // superblocks so far (buffer = sbseq & 1)
         uint32_t phases_done = 0;
+        uint32_t bseq = 0;                                   // rmsnorm rebuilds so far (the consumers count the same)
         Prof pf;
         pf.p = p.prof ? p.prof + (size_t)blockIdx.x * 32 : nullptr; pf.t0 = 0ull; pf.trace_slot = -1; pf.ev = nullptr;
         pf.evn = reinterpret_cast<unsigned int*>(smem + p.off_misc) + 31;
@@ -1044,6 +1261,11 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
 #pragma unroll 1
                 for (int sq = 0; sq < n_seqs; ++sq) {
                 const SeqView sv = seq_view<MS>(p, sq);
+                if (kChainOnChainWarp && !RX && (pk == 0 || pk == 2 || pk == 4) && !(p.debug_skip & 8)) {
+                    // the rmsnorm rebuild of this phase's input: the sum-of-squares chain runs here, following the consumers' polls
+                    sumsq_service<GS>(reinterpret_cast<const float*>(smem + p.off_xt), reinterpret_cast<float*>(smem + p.off_misc), p.dim, bseq, lane);
+                    ++bseq;
+                }
                 uint2* out = (pk == 0) ? sv.qkvt : (pk == 2) ? sv.hdt : sv.x1t;
                 const uint32_t tag_out = tl + ((pk == 0) ? 1u : (pk == 1) ? 4u : (pk == 2) ? 5u : 6u);
                 struct { int rb, nt; } pt = {pg[PG_RB], pg[PG_NT]};
@@ -1129,6 +1351,9 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
     }
 
     // ================= consumers =================
+#ifndef FL_NO_SETMAXNREG
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(kRegsConsumer));
+#endif
     uint8_t* xq = smem + p.off_xq;
     float* xs = reinterpret_cast<float*>(smem + p.off_xs);
     float* xt = reinterpret_cast<float*>(smem + p.off_xt);
@@ -1140,6 +1365,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
     uint32_t sc = 0, cseq = 0, sbseq = 0;      // stages / K chunks / superblocks so far
     uint32_t sb_sl = 0, sb_pr = 0;             // ring slot and parity of stage `sc`, advanced incrementally
     uint32_t phases_drained = 0;
+    uint32_t bseq = 0;                         // rmsnorm rebuilds so far
     Prof pf;
     pf.p = p.prof ? p.prof + (size_t)blockIdx.x * 32 : nullptr;
     pf.t0 = pf.p ? (unsigned long long)clock64() : 0ull;
@@ -1173,7 +1399,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
         for (int pi = 0; pi < n_phases; ++pi) {
             const int layer = pi >> 2, pk = (pi == n_phases - 1) ? 4 : (pi & 3);
             const uint32_t tl = tbase + (uint32_t)layer * kTagsPerLayer;
-            // tags: +0 layer input (= +6 of the previous layer), +1 qkv, +2 scores, +3 attention out, +4 x1 after Wo, +5 hd, +6 x1 after W2
+            // tags: +0 layer input (= +6 of the previous layer), +1 qkv, +2 scores, +3 attention out, +4 x1 after Wo, +5 hd, +6 x1 after W2, +7 quantised hd
             const uint32_t tag_x_in = (layer == 0) ? tbase : tl - kTagsPerLayer + 6u;
 #pragma unroll 1
             for (int sq = 0; sq < n_seqs; ++sq) {
@@ -1195,8 +1421,13 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
                 const uint32_t gpi = MS ? (uint32_t)((step * n_phases + pi) * n_seqs + sq) : (uint32_t)(step * n_phases + pi);
                 const bool no_attn_here = !(attn_cta && !(p.debug_skip & 8));
                 const uint32_t gate_val = gpi + ((!MS && pk == 0 && no_attn_here) ? 2u : 1u);
-                if (!(p.debug_skip & 8)) build_activation<QT, GS, RX>(xq, xs, xt, misc, in, tag_in, gain, K, (pk == 4 && blockIdx.x == 0) ? p.tap_norm : nullptr, tid, pf,
-                                                                  (!MS && pk == 1) ? nullptr : gate, gate_val);
+                if (!(p.debug_skip & 8) && pk == 3) {
+                    build_hd<QT, GS>(xq, xs, sv.hdt, sv.hdqt, tag_in, tl + 7u, K, tid, pf, gate, gate_val);
+                } else if (!(p.debug_skip & 8)) {
+                    build_activation<QT, GS, RX>(xq, xs, xt, misc, in, tag_in, gain, K, (pk == 4 && blockIdx.x == 0) ? p.tap_norm : nullptr, tid, pf,
+                                                 (!MS && pk == 1) ? nullptr : gate, gate_val, bseq, phases_drained);
+                    if (gain && !RX) ++bseq;
+                }
             }
             pf.stop(tid, 1);
             pf.log(lane, warp, 7, pk);          // drain starts

@@ -1,0 +1,9 @@
+set -x
+timeout 180 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; rc=$?; tail -3 gpurun_out/smoke.log; echo "smoke rc=$rc"
+if [ $rc -ne 0 ]; then exit 1; fi
+timeout 600 python -m pytest tests/test_forward_gpu.py -q -m gpu --timeout 120 -x > gpurun_out/test_fwd.log 2>&1; rc=$?; tail -15 gpurun_out/test_fwd.log; echo "fwd rc=$rc"
+if [ $rc -ne 0 ]; then exit 1; fi
+timeout 900 python -m pytest tests -q -m gpu --timeout 300 -x > gpurun_out/test_all.log 2>&1; echo "pytest rc=$?"; tail -6 gpurun_out/test_all.log
+timeout 400 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-other-configs > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err; echo "bench rc=$?"; python -c "
+import json;d=json.loads([l for l in open('gpurun_out/bench_quick.json') if l.startswith('{')][-1]);print(d['value'],d['e2e']['value'],d['roofline']['frac'],d['prefill'])"
+FL_PROF_LIB=1 timeout 300 python profiles/phase_times.py 288 64 > gpurun_out/phase_times_v10.log 2>&1; head -24 gpurun_out/phase_times_v10.log
