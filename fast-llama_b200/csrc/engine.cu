@@ -69,6 +69,7 @@ struct fl_engine {
     float* out_norm = nullptr;
     std::vector<PackedMat> qkv, wo, w13, w2;   // per-phase kernels' layout (FL_FLAG_NO_MEGAKERNEL only)
     PackedMat cls;
+    int tile_cap = 32;                            // rows of the tallest weight tile (MegaParams::tile_cap)
     bool want_mega = false;                       // decided in fl_create: which of the two layouts the uploads fill
     std::vector<RkMat> rk_qkv, rk_wo, rk_w13, rk_w2;
     RkMat rk_cls;
@@ -172,7 +173,7 @@ int build_rk_table(fl_engine* e, int kind, int M, int K, int tt) {
     const int nkc = ceil_div(K * es_of(qt), kStageRowBytes);
     std::vector<unsigned long long> off(G + 1, 0);
     for (int c = 0; c < G; ++c) {
-        const RkPart pt = rk_part(M, c, G);
+        const RkPart pt = rk_part(M, c, G, e->tile_cap);
         unsigned long long bytes = 0;
         for (int t = 0; t < pt.nt; ++t) { int lr0, R; rk_tile(pt, t, lr0, R); bytes += (unsigned long long)tt * nkc * rk_stage_bytes(qt, gs, R); }
         off[c + 1] = off[c] + bytes;
@@ -193,7 +194,7 @@ int alloc_rk(fl_engine* e, RkMat& m, int kind) {
 
 bool mega_supported(const fl_config& c, int n_sms) {
     const int max_rows = (c.vocab_size > c.hidden_dim ? c.vocab_size : c.hidden_dim) / n_sms + 1;     // rows of a CTA: at most kGeomMaxTiles tiles
-    if (max_rows > kGeomMaxTiles * kTileRows || c.dim + 2 * c.head_size * c.n_kv_heads > n_sms * kGeomMaxTiles * kTileRows) return false;
+    if (max_rows > kGeomMaxTiles * 16 || c.dim + 2 * c.head_size * c.n_kv_heads > n_sms * kGeomMaxTiles * kTileRows) return false;
     return !(c.flags & FL_FLAG_NO_MEGAKERNEL) && c.n_heads <= n_sms && c.dim <= 6144;
 }
 
@@ -445,7 +446,8 @@ int setup_mega(fl_engine* e) {
     p.n_vchunks = (int)(vbytes / v_chunk_bytes) > 16 ? 16 : (int)(vbytes / v_chunk_bytes);
     int max_smem = 0;
     CK(e, cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, e->device));
-    const size_t slot_bytes = (size_t)rk_stage_bytes(qt, gs, kTileRows);
+    const size_t slot_bytes = (size_t)rk_stage_bytes(qt, gs, e->tile_cap);
+    p.tile_cap = e->tile_cap; p.slot_bytes = (int)slot_bytes;
     int n_slots = (int)(((size_t)max_smem - off - 1024) / (slot_bytes + 16));
     if (n_slots > 32) n_slots = 32;
     if (n_slots < 4) return set_err(e, FL_ERR_UNSUPPORTED, "megakernel: not enough shared memory for the weight ring (%d slots)", n_slots);
@@ -745,11 +747,7 @@ int fl_create(const fl_config* cfg, int device, fl_engine** out) {
     CKF(cudaGetDeviceProperties(&prop, device));
     e->n_sms = prop.multiProcessorCount;
     CKF(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
-#ifdef FL_CPH2
-    e->cph = 2;     // A/B build
-#else
-    e->cph = 4;
-#endif
+    e->cph = 4;     // measured in round 2: 2 CTAs per head 412.6 against 431.0 tokens/s (7B, ctx 33-543)
     while (e->cph > 1 && (c.n_heads * e->cph > e->n_sms || c.head_size / e->cph < 16)) e->cph /= 2;
 
     const int L = c.n_layers, kv_dim = c.head_size * c.n_kv_heads;
@@ -763,6 +761,16 @@ int fl_create(const fl_config* cfg, int device, fl_engine** out) {
     e->want_mega = mega_supported(c, e->n_sms);
     if (e->want_mega) {
         e->rk_qkv.resize(L); e->rk_wo.resize(L); e->rk_w13.resize(L); e->rk_w2.resize(L);
+        {   // tile cap = the tallest tile of the four layer matrices under the 32-lane limit (rk_part)
+            int cap = 1;
+            const int Ms[4] = {c.dim + 2 * kv_dim, c.dim, c.hidden_dim, c.dim};
+            for (int M : Ms)
+                for (int cta = 0; cta < e->n_sms; ++cta) {
+                    const RkPart pt = rk_part(M, cta, e->n_sms, kTileRows);
+                    for (int t = 0; t < pt.nt; ++t) { int lr0, R; rk_tile(pt, t, lr0, R); cap = R > cap ? R : cap; }
+                }
+            e->tile_cap = cap;
+        }
         int rc = build_rk_table(e, RK_QKV, c.dim + 2 * kv_dim, c.dim, 1);
         if (!rc) rc = build_rk_table(e, RK_WO, c.dim, c.dim, 1);
         if (!rc) rc = build_rk_table(e, RK_W13, c.hidden_dim, c.dim, 2);
@@ -966,7 +974,7 @@ int fl_upload(fl_engine* e, int kind, int layer, const void* q, const float* sca
                 }
                 int rc = dispatch_q(qt, gs, [&](auto QT, auto GS) -> int {
                     pack_rk_kernel<decltype(QT)::value, decltype(GS)::value><<<dim3(e->n_sms, 16), 256, 0, e->stream>>>(
-                        e->staging, d_scales, m->d, e->rk_off[kindk], m_total, cols, row_base, rows, tt, sub);
+                        e->staging, d_scales, m->d, e->rk_off[kindk], m_total, cols, row_base, rows, tt, sub, e->tile_cap);
                     return FL_OK;
                 });
                 if (rc) return set_err(e, rc, "fl_upload: unsupported quantisation");

@@ -112,6 +112,7 @@ struct MegaParams {
     int n_steps;
     int cph;                          // CTAs per head (1, 2 or 4)
     int n_slots;                      // ring stages
+    int tile_cap, slot_bytes;         // rows of the tallest tile; bytes of a ring slot = one stage of such a tile
     int debug_skip;                   // profiling experiments only (FL_DEBUG_SKIP): 1 = consumers release stages without computing
     int window;                       // max stages in flight (issued, not yet landed); >= n_slots: no limit
     uint32_t epoch;                   // tags of this launch are epoch + 1 ... epoch + n_steps * (n_layers + 1) * 8
@@ -243,7 +244,7 @@ struct Prof {
 
 // ---------------------------------------------------------------------------------------------- schedule
 constexpr int kStageRowBytes = 256;        // bytes of one row in one stage
-constexpr int kTileRows = 32;              // one lane per row
+constexpr int kTileRows = 32;              // one lane per row: the most a tile can hold (an engine's tiles are capped at MegaParams::tile_cap <= 32)
 
 template <int QT, int GS>
 struct Rk {
@@ -253,17 +254,19 @@ struct Rk {
     static constexpr int PPG = GS * ES / 16;                      // 16-byte pieces per group
     static constexpr int PIECES = kStageRowBytes / 16;
     __host__ __device__ static constexpr int stage_bytes(int R) { return R * kStageRowBytes + ((R * GPS * 4 + 15) & ~15); }
-    static constexpr int SLOT_BYTES = stage_bytes(kTileRows);
     static_assert(GS == 64 || (GS == 32 && QT == Q_INT8), "group size");
 };
 
 // rows of CTA c and their cut into tiles (host and device agree on this arithmetic; the packer bakes it into the layout)
 struct RkPart { int rb, nr, nt; };
-__host__ __device__ inline RkPart rk_part(int M, int c, int G) {
+// cap: the engine's tile height.  The ring's slots are as large as the largest stage, so the cap is the largest tile the four
+// matrices of a layer need under the 32-lane limit (28 rows at the 7B shape: 23 slots instead of 20 in the same shared memory),
+// and the classifier, whose rows per CTA would cut into taller tiles (31), is cut with the same cap.
+__host__ __device__ inline RkPart rk_part(int M, int c, int G, int cap) {
     RkPart r;
     r.rb = (int)((long long)M * c / G);
     r.nr = (int)((long long)M * (c + 1) / G) - r.rb;
-    r.nt = (r.nr + kTileRows - 1) / kTileRows;
+    r.nt = (r.nr + cap - 1) / cap;
     return r;
 }
 __host__ __device__ inline void rk_tile(const RkPart& pt, int t, int& lr0, int& R) {
@@ -279,10 +282,10 @@ __host__ __device__ inline void rk_superblock(int nkc, int sk, int j, int& k0, i
 // CTA stream order = issue order: [tile][K chunk][m]; stage = pieces p = 0..15 x R lanes x 16 B, then scales g x R.
 template <int QT, int GS>
 __global__ void pack_rk_kernel(const uint8_t* __restrict__ raw, const float* __restrict__ scales, uint8_t* __restrict__ packed,
-                               const unsigned long long* __restrict__ cta_off, int M_total, int K, int row_base, int rows_src, int tt, int m) {
+                               const unsigned long long* __restrict__ cta_off, int M_total, int K, int row_base, int rows_src, int tt, int m, int cap) {
     using RK = Rk<QT, GS>;
     const int c = blockIdx.x, G = gridDim.x;
-    const RkPart pt = rk_part(M_total, c, G);
+    const RkPart pt = rk_part(M_total, c, G, cap);
     const int kbytes = K * RK::ES, nkc = (kbytes + kStageRowBytes - 1) / kStageRowBytes, Gtot = K / GS;
     uint8_t* tile_base = packed + cta_off[c];
     for (int t = 0; t < pt.nt; ++t) {
@@ -353,7 +356,7 @@ template <int QT, int GS>
 __device__ __forceinline__ void fill_geometry(const MegaParams& p, int* geom, int kind) {
     using RK = Rk<QT, GS>;
     const PhaseShape s = phase_shape(p, kind == 4 ? 4 * p.n_layers : kind);
-    const RkPart pt = rk_part(s.M, blockIdx.x, gridDim.x);
+    const RkPart pt = rk_part(s.M, blockIdx.x, gridDim.x, p.tile_cap);
     int* g = geom + kind * kGeomStride;
     g[PG_M] = s.M; g[PG_K] = s.K; g[PG_TT] = s.tt; g[PG_RB] = pt.rb; g[PG_NR] = pt.nr; g[PG_NT] = pt.nt;
     g[PG_NKC] = ceil_div(s.K * RK::ES, kStageRowBytes);
@@ -563,6 +566,17 @@ __device__ __forceinline__ void build_activation(uint8_t* xq, float* xs, float* 
             for (int q = 0; q < LPP; ++q) w[ps][q] = ld_tag2(s + 2 * q);
         }
     }
+    float4 gw[MAXP][PER / 4];
+    if (gain) {
+        // the gain vector (16 KB per layer, L2-resident); measured: fetching it after the poll instead (fewer registers held
+        // across the poll) puts the products behind the chain and costs more than the spill of half of it does
+#pragma unroll
+        for (int ps = 0; ps < MAXP; ++ps) {
+            const int g = min(g0 + ps * GPP, G - 1);        // clamped: always a valid address, unused where the thread has no group
+#pragma unroll
+            for (int q = 0; q < PER / 4; ++q) gw[ps][q] = __ldg(reinterpret_cast<const float4*>(gain + g * GS + sub * PER) + q);
+        }
+    }
     if (chain) {
         // xt lies on top of the pair buffers: this CTA's chain warp must have finished the previous drain
         if (lane == 0) while ((int)(ld_shared_volatile_u32(mw + 29) - pairs_need) < 0) __nanosleep(20);
@@ -606,9 +620,7 @@ __device__ __forceinline__ void build_activation(uint8_t* xq, float* xs, float* 
             }
         }
         if (chain) again = __any_sync(kFull, again) || published < n_pass;
-#ifndef FL_POLL_NOSLEEP
-        if (again) __nanosleep(100);            // a poll that failed is not worth repeating at once: the LSU is shared with warps still working
-#endif
+        if (again) __nanosleep(100);            // a poll that failed is not worth repeating at once: the LSU is shared with warps still working (measured again in round 2: no sleep 427.8 against 431.0 tokens/s)
     } while (again);
     pf.stop(tid, 0);
     pf.log(tid & 31, tid >> 5, 9, 0);
@@ -645,16 +657,24 @@ __device__ __forceinline__ void build_activation(uint8_t* xq, float* xs, float* 
             }
         }
     }
-    // the gain vector (16 KB per layer, L2-resident: every CTA reads it) is fetched only now: next to the 12 in-flight 16-byte
-    // loads of the poll it did not fit the register file, and its latency hides behind the sum-of-squares chain
-    float4 gw[MAXP][PER / 4];
-    if (gain) {
+    // x*w and the group maxima while the chain is still to come (max |(x*w)*r| == (max |x*w|)*r: rounding is monotonic, r > 0)
+    float m[MAXP];
 #pragma unroll
-        for (int ps = 0; ps < MAXP; ++ps) {
-            const int g = min(g0 + ps * GPP, G - 1);        // clamped: always a valid address, unused where the thread has no group
+    for (int ps = 0; ps < MAXP; ++ps) {
+        const int g = g0 + ps * GPP;
+        float mm = 0.0f;
+        if (ps < n_pass && g < G) {
+            if (gain) {
 #pragma unroll
-            for (int q = 0; q < PER / 4; ++q) gw[ps][q] = __ldg(reinterpret_cast<const float4*>(gain + g * GS + sub * PER) + q);
+                for (int q = 0; q < PER / 4; ++q) {                 // x*w, multiply_avx256 x86_simd.cpp:1359
+                    y[ps][4 * q] = __fmul_rn(y[ps][4 * q], gw[ps][q].x); y[ps][4 * q + 1] = __fmul_rn(y[ps][4 * q + 1], gw[ps][q].y);
+                    y[ps][4 * q + 2] = __fmul_rn(y[ps][4 * q + 2], gw[ps][q].z); y[ps][4 * q + 3] = __fmul_rn(y[ps][4 * q + 3], gw[ps][q].w);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < PER; ++i) mm = fmaxf(mm, fabsf(y[ps][i]));
         }
+        m[ps] = group_max8(mm);
     }
     pf.stop(tid, 8);
     float rr = 1.0f;
@@ -686,27 +706,13 @@ __device__ __forceinline__ void build_activation(uint8_t* xq, float* xs, float* 
 #pragma unroll
     for (int ps = 0; ps < MAXP; ++ps) {
         const int g = g0 + ps * GPP;
-        float mm = 0.0f;
-        const bool act = ps < n_pass && g < G;
-        if (act) {
-            if (gain) {
-#pragma unroll
-                for (int q = 0; q < PER / 4; ++q) {                 // x*w, multiply_avx256 x86_simd.cpp:1359
-                    y[ps][4 * q] = __fmul_rn(y[ps][4 * q], gw[ps][q].x); y[ps][4 * q + 1] = __fmul_rn(y[ps][4 * q + 1], gw[ps][q].y);
-                    y[ps][4 * q + 2] = __fmul_rn(y[ps][4 * q + 2], gw[ps][q].z); y[ps][4 * q + 3] = __fmul_rn(y[ps][4 * q + 3], gw[ps][q].w);
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < PER; ++i) mm = fmaxf(mm, fabsf(y[ps][i]));
-        }
-        float m = group_max8(mm);
-        if (act) {
+        if (ps < n_pass && g < G) {
             if (gain) {
 #pragma unroll
                 for (int i = 0; i < PER; ++i) y[ps][i] = __fmul_rn(y[ps][i], rr);     // (x*w)*r
-                m = __fmul_rn(m, rr);                               // max |(x*w)*r| == (max |x*w|)*r: rounding is monotonic, r > 0
+                m[ps] = __fmul_rn(m[ps], rr);
             }
-            quant_store<QT, GS>(xq, xs, y[ps], m, g, sub, tap);
+            quant_store<QT, GS>(xq, xs, y[ps], m[ps], g, sub, tap);
         }
     }
     consumer_sync();
@@ -765,17 +771,21 @@ __device__ __forceinline__ void build_hd(uint8_t* xq, float* xs, const uint2* ra
 #pragma unroll
         for (int i = 0; i < PER / EPW; ++i) st_tag(qt + (size_t)g * PW + sub * (PER / EPW) + i, __uint_as_float(pk[i]), tag_q);
     }
-#ifdef FL_HD_GATE_EARLY
-    // A/B build: this CTA's share of the quantisation is out; let the producer refill the ring during the second hop
-    if (gate) { consumer_sync(); if (tid == 0) st_shared_volatile_u32(gate, gate_val); }
-#endif
+    // this CTA's share of the quantisation is out (the one poll others wait for): the producer may refill the ring during the
+    // second hop - the sync also says that every warp has left the previous phase (measured: 447.6 against 431.0 tokens/s with
+    // the release after the second poll, profiles/r02/ab_hd_gate.log)
+    consumer_sync();
+    if (gate && tid == 0) st_shared_volatile_u32(gate, gate_val);
+    {   // zero the padded tail of the image so padded groups contribute fma(0, 0, acc) == acc
+        const int kpad_bytes = ceil_div(K * RK::ES, kStageRowBytes) * kStageRowBytes;
+        for (int i = K * RK::ES + tid * 4; i < kpad_bytes; i += kConsumerThreads * 4) *reinterpret_cast<uint32_t*>(xq + i) = 0u;
+        for (int i = G + tid; i < (kpad_bytes / kStageRowBytes) * RK::GPS; i += kConsumerThreads) xs[i] = 0.0f;
+    }
     // ---- B: the quantised vector -> shared-memory image.  Word pair i of [payload | scales] lands at word pair i of
     //      [xq | xs] (xs directly behind the payload in index space only: two arrays, one branch).
     const int NP = (NPW + G + 1) >> 1;                      // 16-byte pairs ([NPW payload words][G scale words], the buffer is padded to a pair)
     constexpr int MAXL = 6;                                 // loads per thread per batch (7B: 1462 pairs = 5.7 per thread)
-    const int kpad_bytes = ceil_div(K * RK::ES, kStageRowBytes) * kStageRowBytes;
     uint32_t* xq32 = reinterpret_cast<uint32_t*>(xq);
-    bool first = true;
 #pragma unroll 1
     for (int base = 0; base < NP; base += MAXL * kConsumerThreads) {
         uint4 w[MAXL];
@@ -792,19 +802,10 @@ __device__ __forceinline__ void build_hd(uint8_t* xq, float* xs, const uint2* ra
                 const int pi = base + l * kConsumerThreads + tid;
                 if (pi < NP && (w[l].y != tag_q || (2 * pi + 1 < NPW + G && w[l].w != tag_q))) { w[l] = ld_tag2(qt + 2 * pi); again = true; }
             }
-#ifndef FL_POLL_NOSLEEP
             if (again) __nanosleep(100);
-#endif
         } while (again);
-        if (first) {
-            pf.stop(tid, 0);
-            pf.mark(tid, pf.trace_slot, pf.trace_slot >= 0 && base + MAXL * kConsumerThreads >= NP);
-            consumer_sync();            // every warp has left the previous phase (its drain read the image this build overwrites)
-            if (gate && tid == 0) st_shared_volatile_u32(gate, gate_val);
-            for (int i = K * RK::ES + tid * 4; i < kpad_bytes; i += kConsumerThreads * 4) *reinterpret_cast<uint32_t*>(xq + i) = 0u;
-            for (int i = G + tid; i < (kpad_bytes / kStageRowBytes) * RK::GPS; i += kConsumerThreads) xs[i] = 0.0f;
-            first = false;
-        }
+        pf.stop(tid, 0);
+        pf.mark(tid, pf.trace_slot, pf.trace_slot >= 0 && base + MAXL * kConsumerThreads >= NP);
 #pragma unroll
         for (int l = 0; l < MAXL; ++l) {
             const int wi = 2 * (base + l * kConsumerThreads + tid);
@@ -888,7 +889,9 @@ __device__ __forceinline__ void attention_part(const MegaParams& p, const SeqVie
     // K/V rows of earlier tokens were appended by plain stores of another CTA (part 0 of this head); that CTA's chain warp
     // fenced them before it published tagged rows this CTA has polled since (see the Wo epilogue).  Acquire side of that
     // hand-off, before the cache is read through ld.cg (K) and through the async proxy (V bulk copies):
+#ifndef FL_NO_KV_FENCE      // A/B build only: what the KV hand-off fences cost
     __threadfence();
+#endif
     const int pvt = tid - (kConsumerThreads - DW);          // index inside the PV group (the last DW consumer threads), < 0 for the others
     if (pvt == 0) {
         // the ring also covers the pair buffers: wait until this CTA's chain warp has finished the QKV phase (it trails the
@@ -1222,7 +1225,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
                             }
                             mbar_wait_sleep(&empty[slot], par);
                             mbar_arrive_expect_tx(&full[slot], bytes);
-                            bulk_g2s(ring + (size_t)slot * RK::SLOT_BYTES, src, bytes, &full[slot]);
+                            bulk_g2s(ring + (size_t)slot * p.slot_bytes, src, bytes, &full[slot]);
                             __threadfence_block();                      // the barrier is armed before the count says so
                             st_shared_volatile_u32(issued, ++sc);
                             src += bytes;
@@ -1330,7 +1333,9 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
                 // (plain stores, ordered before this point by the pair-buffer barriers).  The fence makes them visible
                 // device-wide before the tagged rows this warp publishes next (hd, then x1), which every CTA polls before it
                 // reads the cache for the next token.  Off the critical path: the Wo rows are already out.
+#ifndef FL_NO_KV_FENCE
                 if (pk == 1) __threadfence();
+#endif
                 if (lane == 0) st_shared_volatile_u32(reinterpret_cast<uint32_t*>(smem + p.off_misc) + 29, ++phases_done);      // pair buffers are idle until the next drain
                 if (pk == 4) {
                     // per-CTA argmax partial (sampler.cpp:36-46: first index of the strict maximum)
@@ -1471,7 +1476,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
                                 mbar_wait(&full[sl], pr);
                                 pf.stop(tid, (sc + rel + (uint32_t)m - drain_sc0 < 16u) ? 21 : 7);       // waiting for weights = the stream is the limit (21: the stages prefetched during the stall)
                                 pf.log(lane, warp, 2, (int)rel + m);
-                                if (live && !(p.debug_skip & 1)) stage_pairs<QT, GS>(ring + (size_t)sl * RK::SLOT_BYTES, R, xq4 + (k0 + (int)q) * RK::PIECES, xs + (k0 + (int)q) * RK::GPS, lane,
+                                if (live && !(p.debug_skip & 1)) stage_pairs<QT, GS>(ring + (size_t)sl * p.slot_bytes, R, xq4 + (k0 + (int)q) * RK::PIECES, xs + (k0 + (int)q) * RK::GPS, lane,
                                                              pb + m * gstride + (int)q * RK::GPS * 32);
                                 __syncwarp();
                                 if (lane == 0) mbar_arrive(&empty[sl]);
