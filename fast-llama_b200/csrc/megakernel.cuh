@@ -62,13 +62,6 @@ constexpr int kMegaThreads = kConsumerThreads + 128;    // + a third warpgroup: 
 // allocation is 168 per thread, which the consumers' phase loop does not fit without spilling (and with ~227 KB of shared
 // memory carved out a spill is an L2 round trip); the producer and chain warps need far less.  3 x 168 = 88 + 2 x 208 per scheduler (with fewer than 88 ptxas serialises the chain warp's load batches).
 constexpr int kRegsService = 88, kRegsConsumer = 208;
-#ifdef FL_CHAIN_W9
-constexpr bool kChainOnChainWarp = true;      // A/B build: the rmsnorm sum-of-squares chain on the chain warp, following the polls (sumsq_service)
-#else
-// measured (profiles/r02/ab_chain_warp.log): 386 tokens/s with the chain on the chain warp against 438 with the chain on consumer
-// warp 7 after the poll - the overlap with the poll's tail does not pay for whatever slows the chain on warp 9
-constexpr bool kChainOnChainWarp = false;
-#endif
 static_assert(kRegsService + 2 * kRegsConsumer <= 3 * 168, "the CTA's register pool is what the launch allocated: 3 warps x 168 per scheduler (a larger sum deadlocks in setmaxnreg.inc)");
 constexpr int kPairGroups = 64;                          // groups (all sub-streams together) per superblock = per pair buffer (16 KB)
 constexpr int kTagsPerLayer = 8;
@@ -403,31 +396,41 @@ __device__ __forceinline__ void quant_store(uint8_t* xq, float* xs, const float 
 
 // simd::rmsnorm's sum of squares (x86_simd.cpp:941-962 via the __AVX2 typo at :1093): four FMA chains over x[4i+j], then
 // 0 + l0 + l1 + l2 + l3.  xt is the TRANSPOSED fp32 vector in shared memory: xt[j * n/4 + i] = x[4i + j], so lane j
-// streams its chain with 16-byte loads, double-buffered (5.4 cycles per dependent step on B200, profiles/r01: 2x the
+// streams its chain with 16-byte loads, double-buffered (profiles/r01: 2x the
 // natural-layout version).  Called by one warp; returns the value in all its lanes.
 __device__ __forceinline__ float sumsq_chain_t(const float* xt, int n, int lane) {
     float acc = 0.0f;
     if (lane < 4) {
         const int nv = n >> 4;                                // float4s per chain
         const float4* p = reinterpret_cast<const float4*>(xt + lane * (n >> 2));
-        constexpr int B = 8;
-        int i = 0;
-        if (nv >= B) {
-            float4 cur[B], nxt[B];
+        auto fma8 = [](const float4 (&v)[8], float acc) {
 #pragma unroll
-            for (int u = 0; u < B; ++u) cur[u] = p[u];
-#pragma unroll 1
-            for (; i + B <= nv; i += B) {
-#pragma unroll
-                for (int u = 0; u < B; ++u) nxt[u] = p[min(i + B + u, nv - 1)];
-#pragma unroll
-                for (int u = 0; u < B; ++u) {
-                    acc = __fmaf_rn(cur[u].x, cur[u].x, acc); acc = __fmaf_rn(cur[u].y, cur[u].y, acc);
-                    acc = __fmaf_rn(cur[u].z, cur[u].z, acc); acc = __fmaf_rn(cur[u].w, cur[u].w, acc);
-                }
-#pragma unroll
-                for (int u = 0; u < B; ++u) cur[u] = nxt[u];
+            for (int u = 0; u < 8; ++u) {
+                acc = __fmaf_rn(v[u].x, v[u].x, acc); acc = __fmaf_rn(v[u].y, v[u].y, acc);
+                acc = __fmaf_rn(v[u].z, v[u].z, acc); acc = __fmaf_rn(v[u].w, v[u].w, acc);
             }
+            return acc;
+        };
+        int i = 0;
+        if (nv >= 8) {
+            // two register sets in turn (no copies, no clamped indices): the loads of one unit of 8 float4s are in flight
+            // while the other unit's 32 dependent FMAs run
+            float4 a[8], b[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) a[u] = p[u];
+#pragma unroll 1
+            while (i + 16 <= nv) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) b[u] = p[i + 8 + u];
+                acc = fma8(a, acc);
+                if (i + 24 <= nv) {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) a[u] = p[i + 16 + u];
+                }
+                acc = fma8(b, acc);
+                i += 16;
+            }
+            if (i + 8 <= nv) { acc = fma8(a, acc); i += 8; }
         }
 #pragma unroll 1
         for (; i < nv; ++i) {
@@ -445,105 +448,26 @@ __device__ __forceinline__ float sumsq_chain_t(const float* xt, int n, int lane)
     return res;
 }
 
-// In the persistent kernel the same chain is run by the CHAIN WARP (idle between two drains) while the consumer warps are still polling: consumer warp w
-// stores its share of the transposed vector pass by pass (a pass of a warp = 4 quantisation groups = one SEGMENT of
-// 4 * GS consecutive elements; segments in element order: pass-major, then warp) and publishes (build << 8 | passes stored) in
-// seg_flags[w].  The chain follows that frontier in element order, so it has usually covered most of the vector when the last
-// word of the exchange arrives - instead of starting there.  Result (the rmsnorm scale) -> misc[18], then misc word 19 = build + 1.
-template <int GS>
-__device__ __forceinline__ void sumsq_service(const float* xt, float* misc, int K, uint32_t bseq, int lane) {
-    uint32_t* mw = reinterpret_cast<uint32_t*>(misc);
-    const uint32_t* seg_flags = mw + 416;
-    constexpr int FPG = GS / 16;                            // float4s per chain lane per group
-    const int G = K / GS;
-    const int total = K >> 4;                               // float4s per chain lane
-    const float4* pl = reinterpret_cast<const float4*>(xt + (lane & 3) * (K >> 2));      // lanes 4..31 shadow lanes 0..3 (no divergence)
-    int ready = 0, seg = 0;                                 // float4s known to be stored; next segment to look at
-    // The flag of the next segment is READ at the start of a unit and LOOKED AT after the unit's FMAs, so its latency stays off
-    // the chain; only when the loads of the next unit would pass the frontier does the warp spin.  No fence on this side: the
-    // data loads are issued after the flag value has arrived (the writer fences between its stores and its flag).
-    auto flag_need = [&](int sg) { return (bseq << 8) | (uint32_t)((sg >> 3) + 1); };
-    auto take = [&]() { ready += min(4, G - 4 * seg) * FPG; ++seg; };
-    auto wait_for = [&](int upto) {
-        while (ready < upto) {
-            while ((int)(ld_shared_volatile_u32(seg_flags + (seg & 7)) - flag_need(seg)) < 0) { }
-            take();
-        }
-    };
-    auto fma4 = [](const float4 (&v)[4], float acc) {
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            acc = __fmaf_rn(v[u].x, v[u].x, acc); acc = __fmaf_rn(v[u].y, v[u].y, acc);
-            acc = __fmaf_rn(v[u].z, v[u].z, acc); acc = __fmaf_rn(v[u].w, v[u].w, acc);
-        }
-        return acc;
-    };
-    float acc = 0.0f;
-    int i = 0;                                              // float4s consumed
-    if (total >= 4) {
-        float4 a[4], b[4];
-        wait_for(total < 8 ? total : 8);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) a[u] = pl[u];
-        int ps = seg;                                       // the segment whose flag `f` was read for
-        uint32_t f = ld_shared_volatile_u32(seg_flags + (seg & 7));
-        // one unit: `cur` holds float4s [i, i + 4) and the next unit's data are known to be stored.  Everything between the
-        // loads and the closing branch is one basic block, so the bookkeeping interleaves with the dependent FMAs.
-        auto step = [&](const float4 (&cur)[4], float4 (&nxt)[4]) {
-            const bool more = i + 8 <= total;
-            if (more) {
-#pragma unroll
-                for (int u = 0; u < 4; ++u) nxt[u] = pl[i + 4 + u];
-            }
-            acc = fma4(cur, acc);
-            // the flag read during the previous unit; then read the next one
-            if (ps == seg && 4 * seg < G && (int)(f - flag_need(seg)) >= 0) take();
-            ps = seg;
-            f = ld_shared_volatile_u32(seg_flags + (seg & 7));
-            i += 4;
-            if (more && i + 8 <= total && ready < i + 8) wait_for(i + 8);
-            return more;
-        };
-#pragma unroll 1
-        while (true) {
-            if (!step(a, b)) break;
-            if (!step(b, a)) break;
-        }
-    }
-#pragma unroll 1
-    for (; i < total; ++i) {
-        wait_for(i + 1);
-        const float4 v = pl[i];
-        acc = __fmaf_rn(v.x, v.x, acc); acc = __fmaf_rn(v.y, v.y, acc);
-        acc = __fmaf_rn(v.z, v.z, acc); acc = __fmaf_rn(v.w, v.w, acc);
-    }
-    const float l0 = __shfl_sync(kFull, acc, 0), l1 = __shfl_sync(kFull, acc, 1);
-    const float l2 = __shfl_sync(kFull, acc, 2), l3 = __shfl_sync(kFull, acc, 3);
-    float res = __fadd_rn(0.0f, l0);
-    res = __fadd_rn(res, l1);
-    res = __fadd_rn(res, l2);
-    res = __fadd_rn(res, l3);
-    if (lane == 0) {
-        misc[18] = rms_scale(res, K);
-        __threadfence_block();
-        st_shared_volatile_u32(mw + 19, bseq + 1u);
-    }
-}
-
 // Rebuild the quantised activation vector of a phase in shared memory (every CTA, redundantly) from the tagged vector
 // `src` (K = dim elements: the W2 input goes through build_hd below), waiting for every word to carry `tag`.
 //   gain != NULL: y = (x*w)*r, r = 1/sqrt(mean(x^2)+eps) (simd::rmsnorm, x86_simd.cpp:1754);  gain == NULL: y = x.
 // Thread layout: 8 lanes per quantisation group, 32 groups per pass, at most MAXP passes (K <= 24 * 256 = 6144, checked by
-// the host): all loads are in flight before the first tag is looked at, and the values wait in registers.
-// The rmsnorm case validates its words pass by pass and hands them to the chain warp through the transposed vector xt
-// (sumsq_service), so the sum-of-squares chain overlaps the poll; the products x*w and the group maxima are formed meanwhile
-// (max |(x*w)*r| == (max |x*w|)*r: rounding is monotonic, r > 0).
+// the host); the values wait in registers.
+// Polling.  A CTA that finishes its drain early would otherwise re-read the whole vector (32 KB of tagged words, 12 loads of
+// 16 bytes per thread) once per L2 round trip until the slowest producer has published - several rounds on 148 CTAs, i.e. more
+// L2 traffic than the weights the slow CTAs are still streaming.  So a thread first polls ONE word per pass, the SENTINEL: the
+// last row of the producer CTA that owns its last word (`n_prod` producers own dim * c / n_prod ... rows each and publish
+// a tile's rows with one store instruction).  The lanes of a warp share ~9 sentinels, which coalesce into as many 32-byte
+// sectors: a waiting round costs ~7 KB per CTA instead of 48 KB.  Only when its sentinel carries the tag does the thread
+// load its own words, which are then valid at the first look except at producer boundaries (re-polled as before).  The
+// sentinel's index only has to be SOME later word of the same vector, so it is computed in floating point.
 // RX (FL_FLAG_RELAXED, measurement of what bit-exactness costs): the sum of squares is a tree reduction instead of the
 // reference's four 1024-step FMA chains - same value up to FP32 rounding (~1e-7 relative), NOT the reference's bits.
+// (Round 2 also measured the chain on the otherwise idle chain warp, following the poll pass by pass: 386 against 438 tokens/s,
+// profiles/r02/ab_chain_warp.log; the code is in the history, commit 777712b.)
 template <int QT, int GS, bool RX = false>
 __device__ __forceinline__ void build_activation(uint8_t* xq, float* xs, float* xt, float* misc, const uint2* src, uint32_t tag,
-                                                 const float* gain, int K, float* tap, int tid, Prof& pf, uint32_t* gate, uint32_t gate_val,
-                                                 uint32_t bseq, uint32_t pairs_need) {
+                                                 const float* gain, int K, int n_prod, float* tap, int tid, Prof& pf, uint32_t* gate, uint32_t gate_val) {
     using RK = Rk<QT, GS>;
     constexpr int PER = GS / 8;                 // values per thread per group
     constexpr int LPP = PER / 2;                // 16-byte loads per thread per pass
@@ -554,16 +478,29 @@ __device__ __forceinline__ void build_activation(uint8_t* xq, float* xs, float* 
     const int G = K / GS;
     const int sub = tid & 7, g0 = tid >> 3;
     const int n_pass = ceil_div(G, GPP);
-    uint32_t* mw = reinterpret_cast<uint32_t*>(misc);
-    const bool chain = gain && !RX && kChainOnChainWarp;      // the exact rmsnorm: the chain warp computes the scale
     uint4 w[MAXP][LPP];
+    uint2 sv[MAXP];                             // the sentinel of each pass
+    const float rows_per_prod = (float)K / (float)n_prod, prod_per_row = (float)n_prod / (float)K;
+    auto sentinel = [&](int ps) {
+        const int last = (g0 + ps * GPP) * GS + sub * PER + PER - 1;                    // my last word of the pass
+        const int c = (int)((float)(last + 1) * prod_per_row);                           // ~ its producer
+        return max(last, min(K - 1, (int)((float)(c + 1) * rows_per_prod) - 1));         // ~ that producer's last row
+    };
+    // Sentinels pay where the wait is long (x1 after Wo / W2: every CTA waits for the slowest drain); where the words are
+    // mostly there already (the attention output, the quantised hd) the extra round trip costs more than the saved traffic
+    // (measured with sentinels everywhere: 450 against 461 tokens/s, profiles/r02/ab_sentinel_all.log)
+    const bool use_sentinel = gain != nullptr;
+    uint32_t loaded = use_sentinel ? 0u : 0xffffffffu;      // bit ps: the pass's own words have been requested
 #pragma unroll
     for (int ps = 0; ps < MAXP; ++ps) {
         const int g = g0 + ps * GPP;
         if (ps < n_pass && g < G) {
-            const uint2* s = src + g * GS + sub * PER;
+            if (use_sentinel) sv[ps] = ld_tag1(src + sentinel(ps));
+            else {
+                const uint2* s = src + g * GS + sub * PER;
 #pragma unroll
-            for (int q = 0; q < LPP; ++q) w[ps][q] = ld_tag2(s + 2 * q);
+                for (int q = 0; q < LPP; ++q) w[ps][q] = ld_tag2(s + 2 * q);
+            }
         }
     }
     float4 gw[MAXP][PER / 4];
@@ -577,50 +514,33 @@ __device__ __forceinline__ void build_activation(uint8_t* xq, float* xs, float* 
             for (int q = 0; q < PER / 4; ++q) gw[ps][q] = __ldg(reinterpret_cast<const float4*>(gain + g * GS + sub * PER) + q);
         }
     }
-    if (chain) {
-        // xt lies on top of the pair buffers: this CTA's chain warp must have finished the previous drain
-        if (lane == 0) while ((int)(ld_shared_volatile_u32(mw + 29) - pairs_need) < 0) __nanosleep(20);
-        __syncwarp();
-    }
-    // poll: re-issue the stale loads of every pass; a pass whose words are all valid (and whose predecessors are) is handed
-    // to the chain warp at once
-    float y[MAXP][PER];
-    int published = 0;                          // passes of this warp the chain warp may read (warp-uniform)
     bool again;
     do {
         again = false;
 #pragma unroll
         for (int ps = 0; ps < MAXP; ++ps) {
             const int g = g0 + ps * GPP;
-            bool ok = true;
             if (ps < n_pass && g < G) {
                 const uint2* s = src + g * GS + sub * PER;
+                if (!((loaded >> ps) & 1u)) {
+                    if (sv[ps].y == tag) {
 #pragma unroll
-                for (int q = 0; q < LPP; ++q)
-                    if (w[ps][q].y != tag || w[ps][q].w != tag) { w[ps][q] = ld_tag2(s + 2 * q); ok = false; }
-            }
-            if (!ok) again = true;
-            if (chain && ps < n_pass && published == ps && __all_sync(kFull, ok)) {
-                if (g < G) {
-                    const int e0 = g * GS + sub * PER;                   // multiple of 4
-                    // raw x -> transposed vector for the chain
-                    if constexpr (PER == 8) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            *reinterpret_cast<float2*>(xt + j * (K >> 2) + (e0 >> 2)) = make_float2(__uint_as_float(j & 1 ? w[ps][j >> 1].z : w[ps][j >> 1].x), __uint_as_float(j & 1 ? w[ps][2 + (j >> 1)].z : w[ps][2 + (j >> 1)].x));
+                        for (int q = 0; q < LPP; ++q) w[ps][q] = ld_tag2(s + 2 * q);
+                        loaded |= 1u << ps;
                     } else {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) xt[j * (K >> 2) + (e0 >> 2)] = __uint_as_float(j & 1 ? w[ps][j >> 1].z : w[ps][j >> 1].x);
+                        sv[ps] = ld_tag1(src + sentinel(ps));
                     }
+                    again = true;               // the words just requested are looked at in the next round
+                } else {
+#pragma unroll
+                    for (int q = 0; q < LPP; ++q)
+                        if (w[ps][q].y != tag || w[ps][q].w != tag) { w[ps][q] = ld_tag2(s + 2 * q); again = true; }
                 }
-                __threadfence_block();
-                __syncwarp();
-                ++published;
-                if (lane == 0) st_shared_volatile_u32(mw + 416 + warp, (bseq << 8) | (uint32_t)published);
             }
         }
-        if (chain) again = __any_sync(kFull, again) || published < n_pass;
-        if (again) __nanosleep(100);            // a poll that failed is not worth repeating at once: the LSU is shared with warps still working (measured again in round 2: no sleep 427.8 against 431.0 tokens/s)
+        // a poll that failed is not worth repeating at once: the LSU is shared with warps still working (measured again in
+        // round 2: no sleep 427.8 against 431.0 tokens/s)
+        if (again) __nanosleep(100);
     } while (again);
     pf.stop(tid, 0);
     pf.log(tid & 31, tid >> 5, 9, 0);
@@ -633,6 +553,7 @@ __device__ __forceinline__ void build_activation(uint8_t* xq, float* xs, float* 
     for (int i = K * RK::ES + tid * 4; i < kpad_bytes; i += kConsumerThreads * 4) *reinterpret_cast<uint32_t*>(xq + i) = 0u;
     for (int i = G + tid; i < (kpad_bytes / kStageRowBytes) * RK::GPS; i += kConsumerThreads) xs[i] = 0.0f;
     // values out of the tagged words (the tags' registers are free from here on)
+    float y[MAXP][PER];
     float ss_part = 0.0f;
 #pragma unroll
     for (int ps = 0; ps < MAXP; ++ps) {
@@ -644,7 +565,7 @@ __device__ __forceinline__ void build_activation(uint8_t* xq, float* xs, float* 
 #pragma unroll
                 for (int i = 0; i < PER; ++i) ss_part = __fmaf_rn(y[ps][i], y[ps][i], ss_part);
             }
-            if (gain && !RX && !kChainOnChainWarp) {
+            if (gain && !RX) {
                 // raw x -> transposed vector for the chain on the serial warp
                 const int e0 = g * GS + sub * PER;                   // multiple of 4
                 if constexpr (PER == 8) {
@@ -687,19 +608,13 @@ __device__ __forceinline__ void build_activation(uint8_t* xq, float* xs, float* 
 #pragma unroll
         for (int w8 = 1; w8 < kConsumerWarps; ++w8) ss = __fadd_rn(ss, misc[8 + w8]);
         rr = rms_scale(ss, K);
-    } else if (gain && !kChainOnChainWarp) {
+    } else if (gain) {
         consumer_sync();
         if (warp == kSerialWarp) {
             const float ss = sumsq_chain_t(xt, K, lane);
             if (lane == 0) misc[18] = rms_scale(ss, K);
         }
         consumer_sync();
-        rr = misc[18];
-    } else if (gain) {
-        // the scale from the chain warp
-        if (lane == 0) while (ld_shared_volatile_u32(mw + 19) != bseq + 1u) { }
-        __syncwarp();
-        __threadfence_block();
         rr = misc[18];
     }
     pf.stop(tid, 9);
@@ -1161,8 +1076,6 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
         reinterpret_cast<uint32_t*>(smem + p.off_misc)[31] = 0u;
         reinterpret_cast<uint32_t*>(smem + p.off_misc)[29] = 0u;      // phases the chain warp has finished
         reinterpret_cast<uint32_t*>(smem + p.off_misc)[20] = 0u;      // prefetch gate: phases (counted over all steps) the producer may stream
-        reinterpret_cast<uint32_t*>(smem + p.off_misc)[19] = 0u;      // rmsnorm rebuilds whose scale the chain warp has delivered
-        for (int i = 0; i < kConsumerWarps; ++i) reinterpret_cast<uint32_t*>(smem + p.off_misc)[416 + i] = 0u;      // per-warp (rebuild << 8 | passes stored)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     const int n_phases = 4 * p.n_layers + 1;
@@ -1247,7 +1160,6 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
         // Follows the consumers' schedule superblock by superblock; lane i owns row i of the current tile.
         uint32_t sbseq = 0;                                  // superblocks so far (buffer = sbseq & 1)
         uint32_t phases_done = 0;
-        uint32_t bseq = 0;                                   // rmsnorm rebuilds so far (the consumers count the same)
         Prof pf;
         pf.p = p.prof ? p.prof + (size_t)blockIdx.x * 32 : nullptr; pf.t0 = 0ull; pf.trace_slot = -1; pf.ev = nullptr;
         pf.evn = reinterpret_cast<unsigned int*>(smem + p.off_misc) + 31;
@@ -1264,11 +1176,6 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
 #pragma unroll 1
                 for (int sq = 0; sq < n_seqs; ++sq) {
                 const SeqView sv = seq_view<MS>(p, sq);
-                if (kChainOnChainWarp && !RX && (pk == 0 || pk == 2 || pk == 4) && !(p.debug_skip & 8)) {
-                    // the rmsnorm rebuild of this phase's input: the sum-of-squares chain runs here, following the consumers' polls
-                    sumsq_service<GS>(reinterpret_cast<const float*>(smem + p.off_xt), reinterpret_cast<float*>(smem + p.off_misc), p.dim, bseq, lane);
-                    ++bseq;
-                }
                 uint2* out = (pk == 0) ? sv.qkvt : (pk == 2) ? sv.hdt : sv.x1t;
                 const uint32_t tag_out = tl + ((pk == 0) ? 1u : (pk == 1) ? 4u : (pk == 2) ? 5u : 6u);
                 struct { int rb, nt; } pt = {pg[PG_RB], pg[PG_NT]};
@@ -1370,7 +1277,6 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
     uint32_t sc = 0, cseq = 0, sbseq = 0;      // stages / K chunks / superblocks so far
     uint32_t sb_sl = 0, sb_pr = 0;             // ring slot and parity of stage `sc`, advanced incrementally
     uint32_t phases_drained = 0;
-    uint32_t bseq = 0;                         // rmsnorm rebuilds so far
     Prof pf;
     pf.p = p.prof ? p.prof + (size_t)blockIdx.x * 32 : nullptr;
     pf.t0 = pf.p ? (unsigned long long)clock64() : 0ull;
@@ -1429,9 +1335,9 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
                 if (!(p.debug_skip & 8) && pk == 3) {
                     build_hd<QT, GS>(xq, xs, sv.hdt, sv.hdqt, tag_in, tl + 7u, K, tid, pf, gate, gate_val);
                 } else if (!(p.debug_skip & 8)) {
-                    build_activation<QT, GS, RX>(xq, xs, xt, misc, in, tag_in, gain, K, (pk == 4 && blockIdx.x == 0) ? p.tap_norm : nullptr, tid, pf,
-                                                 (!MS && pk == 1) ? nullptr : gate, gate_val, bseq, phases_drained);
-                    if (gain && !RX) ++bseq;
+                    // producers of the vector: every CTA owns dim * c / n rows of x1; the attention parts own HS / cph outputs each
+                    build_activation<QT, GS, RX>(xq, xs, xt, misc, in, tag_in, gain, K, (pk == 1) ? n_attn_ctas : (int)gridDim.x,
+                                                 (pk == 4 && blockIdx.x == 0) ? p.tap_norm : nullptr, tid, pf, (!MS && pk == 1) ? nullptr : gate, gate_val);
                 }
             }
             pf.stop(tid, 1);
