@@ -70,6 +70,7 @@ struct fl_engine {
     std::vector<PackedMat> qkv, wo, w13, w2;   // per-phase kernels' layout (FL_FLAG_NO_MEGAKERNEL only)
     PackedMat cls;
     int tile_cap = 32;                            // rows of the tallest weight tile (MegaParams::tile_cap)
+    int longctx_rows = 1 << 30;                   // a launch that can reach a longer context uses the long-context kernel variant
     bool want_mega = false;                       // decided in fl_create: which of the two layouts the uploads fill
     std::vector<RkMat> rk_qkv, rk_wo, rk_w13, rk_w2;
     RkMat rk_cls;
@@ -353,11 +354,12 @@ int enqueue_step(fl_engine* e, int slot, cudaStream_t st, int* n_kernels) {
 
 // multi = true: the variant that walks several sequences per phase (fl_forward_batch)
 template <typename F>
-int dispatch_mega(int qt, int gs, int hs, bool multi, F&& f, bool relaxed = false) {
+int dispatch_mega(int qt, int gs, int hs, bool multi, F&& f, bool relaxed = false, bool longctx = false) {
     // FL_FLAG_RELAXED: only the benchmark shape is instantiated (INT8, group 64, head 128, one sequence per launch)
     if (relaxed && !multi && qt == FL_Q_INT8 && gs == 64 && hs == 128) return f(decode_megakernel<Q_INT8, 64, 128, false, true>);
+    // longctx: the variant whose attention part streams K and V through the weight ring (single sequence per launch only)
 #define FL_MEGA_CASE(QT_, QTC, GS_, HS_) \
-    if (qt == QT_ && gs == GS_ && hs == HS_) return multi ? f(decode_megakernel<QTC, GS_, HS_, true>) : f(decode_megakernel<QTC, GS_, HS_, false>);
+    if (qt == QT_ && gs == GS_ && hs == HS_) return multi ? f(decode_megakernel<QTC, GS_, HS_, true>) : longctx ? f(decode_megakernel<QTC, GS_, HS_, false, false, true>) : f(decode_megakernel<QTC, GS_, HS_, false>);
     FL_MEGA_CASE(FL_Q_INT8, Q_INT8, 64, 128)
     FL_MEGA_CASE(FL_Q_INT8, Q_INT8, 64, 64)
     FL_MEGA_CASE(FL_Q_INT8, Q_INT8, 32, 128)
@@ -429,7 +431,7 @@ int setup_mega(fl_engine* e) {
     p.off_misc = (int)off; off += 2048;
     p.off_att = (int)off; off += al((size_t)c.max_seq_len * 4 + 192, 128);      // + one chunk of zero weights past the last position
     p.off_xs = (int)off; off += al((size_t)nkc_max * gps * 4, 128);
-    p.off_vbars = (int)off; off += 128;
+    p.off_vbars = (int)off; off += 256;      // 32 mbarriers: the V ring of the attention part
     p.off_psrc = (int)off; off += al((size_t)(4 * L + 1) * 8, 128);      // this CTA's weight-stream start of every phase
     p.off_geom = (int)off; off += 5 * kGeomStride * 4;                   // this CTA's tile / superblock geometry of the five phase kinds
     // [activation image | pair buffers]: contiguous, because attention (which uses neither) turns the whole range into its ring
@@ -443,7 +445,7 @@ int setup_mega(fl_engine* e) {
     p.off_pairs = (int)off; p.off_xt = (int)off; off += (pair_bytes > xt_bytes ? pair_bytes : xt_bytes);
     size_t vbytes = off - p.off_vstage;
     if (vbytes < 2 * (size_t)v_chunk_bytes) { off += 2 * v_chunk_bytes - vbytes; vbytes = 2 * v_chunk_bytes; }
-    p.n_vchunks = (int)(vbytes / v_chunk_bytes) > 16 ? 16 : (int)(vbytes / v_chunk_bytes);
+    p.n_vchunks = (int)(vbytes / v_chunk_bytes) > 32 ? 32 : (int)(vbytes / v_chunk_bytes);
     int max_smem = 0;
     CK(e, cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, e->device));
     const size_t slot_bytes = (size_t)rk_stage_bytes(qt, gs, e->tile_cap);
@@ -473,6 +475,8 @@ int setup_mega(fl_engine* e) {
         return FL_OK;
     };
     int rc = dispatch_mega(qt, gs, c.head_size, false, prepare);
+    e->longctx_rows = 2 * p.n_vchunks * kVChunkRows;       // contexts beyond this stage K and V in the weight ring (attention_part, `big`)
+    if (rc == FL_OK && c.max_seq_len > e->longctx_rows) rc = dispatch_mega(qt, gs, c.head_size, false, prepare, false, true);
     if (rc == FL_OK && (c.flags & FL_FLAG_RELAXED)) rc = dispatch_mega(qt, gs, c.head_size, false, prepare, true);
     if (rc == FL_OK && c.max_seqs > 1) rc = dispatch_mega(qt, gs, c.head_size, true, prepare);
     if (rc == FL_ERR_UNSUPPORTED) return set_err(e, rc, "megakernel: unsupported quant/group/head combination");
@@ -516,7 +520,12 @@ int launch_mega(fl_engine* e, int slot, int n_steps, int n_seqs = 1) {
         if (s != cudaSuccess) return set_err(e, FL_ERR_CUDA, "megakernel launch: %s", cudaGetErrorString(s));
         e->launches += 1;
         return FL_OK;
-    }, (c.flags & FL_FLAG_RELAXED) != 0);
+    }, (c.flags & FL_FLAG_RELAXED) != 0, 
+#ifdef FL_NO_LONGCTX       // A/B build: never the long-context variant
+       false);
+#else
+       n_seqs == 1 && !(c.flags & FL_FLAG_RELAXED) && e->h_pos[slot] > e->longctx_rows);
+#endif
 }
 
 int run_step(fl_engine* e, int slot) {
@@ -1072,6 +1081,7 @@ int fl_forward(fl_engine* e, int seq_slot, const int32_t* tokens, int n_tokens, 
             // n_out restarts at the last token of the call, so out_tokens[0] is the token sampled after the whole input
             set_state_kernel<<<1, 1, 0, e->stream>>>(e->states + seq_slot, e->in_tokens, i, pos + i, n_tokens, i == n_tokens - 1);
             e->launches += 1;
+            e->h_pos[seq_slot] = pos + i + 1;       // launch_mega picks the long-context kernel variant by the position reached
             int rc = run_step(e, seq_slot);
             if (rc) return rc;
         }

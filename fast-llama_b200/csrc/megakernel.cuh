@@ -763,7 +763,74 @@ __device__ __forceinline__ void stage_pairs(const uint8_t* sp, int R, const uint
 // sections - softmax's sum and the PV chains - run as register-staged FP32 chains.
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-template <int HS, bool RX = false>
+// The K sweep of a long context (attention_part, `big`): the part's cached K rows [tb, kc_end) arrive through the weight ring
+// in chunks of 32 rows (issue_k in attention_part filled the first NKC slots); warp w takes rows 4w .. 4w + 3 of every chunk,
+// 8 lanes per row as in the register path, and warp 0 refills the slot of chunk c - 1 once every warp has reported it done.
+struct KSweepOut { uint32_t ph; float mloc; };
+template <int HS>
+__device__ __forceinline__ KSweepOut k_sweep_ring(float* kring, uint64_t* vfull, uint32_t* kprog, const float* kc, const float* q_s, const float* k_s,
+                                               float* att, uint2* att_g, int tb, int kc_end, int te, int pos, int NKC, int nkch, int cph,
+                                               float attn_scale, uint32_t tag_score, uint32_t ph, int tid) {
+    constexpr int EPL = HS / 8, KR = 32, KROW = HS + 4;
+    const int warp = tid >> 5, lane = tid & 31, rr = lane >> 3, j = lane & 7;
+    float mloc = -INFINITY;
+    const float* qj = q_s + j;
+    auto score = [&](const float4 (&k4)[EPL / 4], int t, bool live) {
+        float acc = 0.0f;
+#pragma unroll
+        for (int q = 0; q < EPL / 4; ++q) {
+            acc = __fmaf_rn(k4[q].x, qj[8 * (4 * q)], acc);
+            acc = __fmaf_rn(k4[q].y, qj[8 * (4 * q + 1)], acc);
+            acc = __fmaf_rn(k4[q].z, qj[8 * (4 * q + 2)], acc);
+            acc = __fmaf_rn(k4[q].w, qj[8 * (4 * q + 3)], acc);
+        }
+        float tot = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) tot = __fadd_rn(tot, __shfl_sync(kFull, acc, (rr << 3) + k));
+        if (j == 0 && live) {
+            const float sc = __fmul_rn(tot, attn_scale);                // att.multiply(attn_scale), transformer.cpp:443
+            att[t] = sc;
+            mloc = fmaxf(mloc, sc);
+            if (cph > 1) st_tag(att_g + t, sc, tag_score);
+        }
+    };
+    auto issue_k = [&](int c) {                             // warp 0, all lanes (same as attention_part's)
+        const int slot = c % NKC, t0 = tb + c * KR, rows = min(KR, kc_end - t0);
+        if (lane == 0) mbar_arrive_expect_tx(&vfull[slot], (uint32_t)(rows * HS * 4));
+        __syncwarp();
+        if (lane < rows) bulk_g2s(kring + ((size_t)slot * KR + lane) * KROW, kc + (size_t)(t0 + lane) * HS, HS * 4, &vfull[slot]);
+    };
+#pragma unroll 1
+    for (int c = 0; c < nkch; ++c) {
+        const int slot = c % NKC;
+        mbar_wait(&vfull[slot], (ph >> slot) & 1u);
+        ph ^= 1u << slot;
+        const int t = tb + c * KR + warp * 4 + rr;
+        const float4* kp = reinterpret_cast<const float4*>(kring + ((size_t)slot * KR + warp * 4 + rr) * KROW + j * EPL);
+        float4 k4[EPL / 4];
+#pragma unroll
+        for (int q = 0; q < EPL / 4; ++q) k4[q] = (t < kc_end) ? kp[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+        score(k4, t, t < kc_end);
+        __syncwarp();
+        if (lane == 0) st_shared_volatile_u32(kprog + warp, (uint32_t)c + 1u);
+        if (warp == 0 && c >= 1 && c - 1 + NKC < nkch) {
+            // every warp has finished chunk c - 1: refill its slot
+            while (!__all_sync(kFull, lane >= kConsumerWarps || (int)ld_shared_volatile_u32(kprog + lane) >= c)) { }
+            issue_k(c - 1 + NKC);
+        }
+    }
+    if (pos >= tb && pos < te && warp == kConsumerWarps - 1) {
+        // the new token's key, from the RoPE'd row in shared memory
+        float4 k4[EPL / 4];
+#pragma unroll
+        for (int q = 0; q < EPL / 4; ++q)
+            k4[q] = make_float4(k_s[8 * (4 * q) + j], k_s[8 * (4 * q + 1) + j], k_s[8 * (4 * q + 2) + j], k_s[8 * (4 * q + 3) + j]);
+        score(k4, pos, rr == 0);
+    }
+    return KSweepOut{ph, mloc};
+}
+
+template <int HS, bool RX = false, bool LC = false>
 __device__ __forceinline__ void attention_part(const MegaParams& p, const SeqView sv, uint8_t* smem, int layer, int qh, int part, int pos, int bs,
                                                uint32_t tag_qkv, uint32_t tag_score, uint32_t tag_out, uint32_t phases_drained, int tid, Prof& pf,
                                                uint32_t* gate = nullptr, uint32_t gate_val = 0u) {
@@ -775,11 +842,9 @@ __device__ __forceinline__ void attention_part(const MegaParams& p, const SeqVie
     float* k_s = q_s + HS;
     float* v_s = k_s + HS;
     float* red = reinterpret_cast<float*>(smem + p.off_misc);
-    uint32_t* vcount = reinterpret_cast<uint32_t*>(smem + p.off_misc) + 28;      // V chunks streamed so far by this CTA (ring position)
-    float* v_stage = reinterpret_cast<float*>(smem + p.off_vstage);
+    uint32_t* vphase = reinterpret_cast<uint32_t*>(smem + p.off_misc) + 28;      // bit s: parity of the next completion of V barrier s
     uint64_t* vfull = reinterpret_cast<uint64_t*>(smem + p.off_vbars);
     constexpr int VR = kVChunkRows;
-    const int NCH = p.n_vchunks;
 
     const int hgs = p.n_heads / p.n_kv_heads;
     const int kvh = qh / hgs, g = qh % hgs;
@@ -793,10 +858,27 @@ __device__ __forceinline__ void attention_part(const MegaParams& p, const SeqVie
 
     // ---- V ring: chunk c = cached rows [c*VR, min(pos, (c+1)*VR)) of the column block, one bulk copy each
     const int n_chunks = ceil_div(pos, VR);                 // the new row (t == pos) comes from v_s
-    const uint32_t vbase = *vcount;
+    // Staging area.  Short contexts: the activation image + pair buffers (idle during attention), ~10 chunks, and the producer
+    // refills the weight ring with Wo / W13 while softmax and PV run.  LONG contexts (more than twice that): the weight ring
+    // itself - it is empty between the QKV drain and the moment this function releases the producer's gate - so up to 32 chunks
+    // (~170 KB) of V are in flight and the sweep runs at the SM's ingest rate instead of at 43 KB per round trip; the gate then
+    // opens after PV (Wo's 2.4 us of prefetch are noise next to a 10-30 us sweep).  Needs the gate: not in multi-sequence launches.
+    // LC: the long-context code exists only in the kernel variant the host launches when a sequence can get that far (its
+    // registers and instructions would otherwise tax the short-context path: +430 bytes of spills in the phase loop)
+    const bool big = LC && gate != nullptr && n_chunks > 2 * p.n_vchunks;
+#ifdef FL_LONG_K
+    constexpr bool kRingK = true;
+#else
+    // measured (profiles/r02/longctx_ab.log): with K through the ring as well the 13B long-context case ran at 106.6 tokens/s
+    // against 138.8 with K in registers - one 512-byte bulk copy per row (the padded row stride needs them) is too fine a
+    // grain for the copy engine; the code stays for the A/B build
+    constexpr bool kRingK = false;
+#endif
+    const bool bigk = big && kRingK;
+    float* v_stage = reinterpret_cast<float*>(smem + (big ? p.off_ring : p.off_vstage));
+    const int NCH = big ? min(32, (p.n_slots * p.slot_bytes) / (VR * DW * 4)) : p.n_vchunks;
     auto issue_v = [&](int c) {                             // one thread
-        const uint32_t gidx = vbase + (uint32_t)c;
-        const uint32_t slot = gidx % (uint32_t)NCH;
+        const uint32_t slot = (uint32_t)c % (uint32_t)NCH;
         const uint32_t bytes = (uint32_t)((min(VR, pos - c * VR) + 3) >> 2) * DW * 16;      // whole blocks of 4 positions
         mbar_arrive_expect_tx(&vfull[slot], bytes);
         bulk_g2s(v_stage + (size_t)slot * VR * DW, vc + (size_t)c * VR * DW, bytes, &vfull[slot]);
@@ -808,7 +890,8 @@ __device__ __forceinline__ void attention_part(const MegaParams& p, const SeqVie
     __threadfence();
 #endif
     const int pvt = tid - (kConsumerThreads - DW);          // index inside the PV group (the last DW consumer threads), < 0 for the others
-    if (pvt == 0) {
+    uint32_t ph = *vphase;                                  // every thread follows the barriers' phases (same waits in the same order)
+    if (pvt == 0 && !bigk) {
         // the ring also covers the pair buffers: wait until this CTA's chain warp has finished the QKV phase (it trails the
         // consumers by one superblock at most)
         while ((int)(ld_shared_volatile_u32(reinterpret_cast<uint32_t*>(smem + p.off_misc) + 29) - phases_drained) < 0) __nanosleep(50);
@@ -821,7 +904,30 @@ __device__ __forceinline__ void attention_part(const MegaParams& p, const SeqVie
     const int per = ceil_div(ceil_div(n, cph), 4) * 4;
     const int tb = part * per, te = min(n, tb + per);
     const int rr = lane >> 3, j = lane & 7;
-    constexpr int UU = 3;
+    // long contexts: the part's cached K rows [tb, min(te, pos)) stream through the weight ring as well (before V, which is
+    // requested once the sweep is over): chunks of 32 rows, one 512-byte bulk copy per row into a row stride of HS * 4 + 16
+    // bytes (conflict-free LDS.128 for 4 keys x 8 lanes), NKC chunks in flight instead of one register batch per round trip
+    constexpr int KR = 32, KROW = HS + 4;                   // rows per K chunk; floats per staged row
+    const int kc_end = min(te, pos);
+    const int nkch = bigk ? ceil_div(max(kc_end - tb, 0), KR) : 0;
+    const int NKC = bigk ? min(32, (p.n_slots * p.slot_bytes) / (KR * KROW * 4)) : 1;
+    float* kring = reinterpret_cast<float*>(smem + p.off_ring);
+    uint32_t* kprog = reinterpret_cast<uint32_t*>(smem + p.off_misc) + 416;     // [warp] K chunks this warp has finished
+    auto issue_k = [&](int c) {                             // warp 0, all lanes
+        const int slot = c % NKC, t0 = tb + c * KR, rows = min(KR, kc_end - t0);
+        if (lane == 0) mbar_arrive_expect_tx(&vfull[slot], (uint32_t)(rows * HS * 4));
+        __syncwarp();
+        if (lane < rows) bulk_g2s(kring + ((size_t)slot * KR + lane) * KROW, kc + (size_t)(t0 + lane) * HS, HS * 4, &vfull[slot]);
+    };
+    if (bigk) {
+        if (lane == 0) kprog[warp] = 0u;
+        if (warp == 0) {
+            fence_proxy_async();                            // the ring held weights the generic proxy has just read
+            asm volatile("fence.proxy.async.global;" ::: "memory");      // the K rows were written through the generic proxy
+            for (int c = 0; c < min(NKC, nkch); ++c) issue_k(c);
+        }
+    }
+    constexpr int UU = 3;                      // key batches per round trip: 96 keys per CTA (6 batches in the long-context variant measured slower: 122 vs 138 tokens/s at the 13B shape)
     float4 kv[UU][EPL / 4];
     auto load_k = [&](int base) {
 #pragma unroll
@@ -837,7 +943,7 @@ __device__ __forceinline__ void attention_part(const MegaParams& p, const SeqVie
             }
         }
     };
-    load_k(tb);
+    if (!bigk) load_k(tb);
 
     // ---- q, k, v rows of this head: 3 * HS tagged words, one 16-byte load (= one RoPE pair) per thread
     // RoPE + KV append (rope_v2 tf_operators.cpp:355-402; transformer.cpp:431-439)
@@ -879,7 +985,10 @@ __device__ __forceinline__ void attention_part(const MegaParams& p, const SeqVie
     // ---- scores for this part's keys: float dot_product_avx256 (x86_simd.cpp:1447-1468): 8 FMA chains, then 0 + l0 + ... + l7
     uint2* att_g = sv.score_t + (size_t)qh * p.score_stride;
     float mloc = -INFINITY;                        // running maximum of the scores this thread stores (softmax's max, fused)
-    {
+    if (bigk) {
+        const KSweepOut ko = k_sweep_ring<HS>(kring, vfull, kprog, kc, q_s, k_s, att, att_g, tb, kc_end, te, pos, NKC, nkch, cph, p.attn_scale, tag_score, ph, tid);
+        ph = ko.ph; mloc = ko.mloc;
+    } else {
         const float* qj = q_s + j;                 // q values of this AVX lane are re-read from shared memory (registers are scarce)
 #pragma unroll 1
         for (int base = tb; base < te; base += kConsumerWarps * 4 * UU) {
@@ -909,7 +1018,7 @@ __device__ __forceinline__ void attention_part(const MegaParams& p, const SeqVie
                     if (cph > 1) st_tag(att_g + t, sc, tag_score);
                 }
             }
-            if (base + kConsumerWarps * 4 * UU < te) load_k(base + kConsumerWarps * 4 * UU);     // contexts beyond 96 * cph keys: one more round trip per batch
+            if (base + kConsumerWarps * 4 * UU < te) load_k(base + kConsumerWarps * 4 * UU);     // contexts beyond 32 * UU * cph keys: one more round trip per batch
         }
     }
     pf.stop(tid, 11);
@@ -930,7 +1039,12 @@ __device__ __forceinline__ void attention_part(const MegaParams& p, const SeqVie
     for (int o = 16; o > 0; o >>= 1) mloc = fmaxf(mloc, __shfl_xor_sync(kFull, mloc, o));
     if (lane == 0) red[warp] = mloc;
     consumer_sync();
-    if (gate && tid == 0) st_shared_volatile_u32(gate, gate_val);       // q / k / v and the scores are in: Wo's prefetch may start (softmax and PV give it time)
+    if (gate && !big && tid == 0) st_shared_volatile_u32(gate, gate_val);       // q / k / v and the scores are in: Wo's prefetch may start (softmax and PV give it time)
+    if (bigk && pvt == 0) {
+        // the K sweep is over in every warp: the ring takes the first wave of V chunks (softmax gives them time to land)
+        fence_proxy_async();
+        for (int c = 0; c < min(NCH, n_chunks); ++c) issue_v(c);
+    }
     pf.stop(tid, 12);
     pf.log(lane, warp, 13, 0);
 
@@ -999,10 +1113,11 @@ __device__ __forceinline__ void attention_part(const MegaParams& p, const SeqVie
     if (pvt >= 0) {
         float o = 0.0f;
         if (n_chunks > 0) {
-            uint32_t slot = vbase % (uint32_t)NCH, par = (vbase / (uint32_t)NCH) & 1u;
+            uint32_t slot = 0u;
             const int qstride = DW * 4;                     // floats between two quads of one head dim
             float4 va[8], wa[8];
-            mbar_wait(&vfull[slot], par);
+            mbar_wait(&vfull[0], ph & 1u);
+            ph ^= 1u;
             pf.stop(tid, 14);                               // waiting for the first V chunk
             {
                 const float* vs = v_stage + (size_t)slot * VR * DW + pvt * 4;
@@ -1014,11 +1129,11 @@ __device__ __forceinline__ void attention_part(const MegaParams& p, const SeqVie
 #pragma unroll 1
             for (int c = 0; c < n_chunks; ++c) {
                 const bool more = c + 1 < n_chunks;
-                uint32_t nslot = slot + 1u, npar = par;
-                if (nslot == (uint32_t)NCH) { nslot = 0u; npar ^= 1u; }
+                uint32_t nslot = slot + 1u;
+                if (nslot == (uint32_t)NCH) nslot = 0u;
                 const float* vs = v_stage + (size_t)nslot * VR * DW + pvt * 4;
                 const float* ws = att + (c + 1) * VR;
-                if (more) mbar_wait(&vfull[nslot], npar);
+                if (more) { mbar_wait(&vfull[nslot], (ph >> nslot) & 1u); ph ^= 1u << nslot; }
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
                     if (fabsf(wa[u].x) > 1e-15f) o = __fmaf_rn(va[u].x, wa[u].x, o);
@@ -1032,7 +1147,7 @@ __device__ __forceinline__ void attention_part(const MegaParams& p, const SeqVie
                     if (DW > 32) asm volatile("bar.sync 2, %0;" :: "r"(DW) : "memory"); else __syncwarp(DW == 32 ? kFull : (kFull << (32 - DW)));      // the PV group is the top DW lanes of its warp
                     if (pvt == 0) issue_v(c + NCH);
                 }
-                slot = nslot; par = npar;
+                slot = nslot;
             }
         }
         {   // the new token's row
@@ -1042,7 +1157,7 @@ __device__ __forceinline__ void attention_part(const MegaParams& p, const SeqVie
         }
         st_tag(sv.attnt + (size_t)qh * HS + d0 + pvt, o, tag_out);
         if (pvt == 0) {
-            *vcount = vbase + (uint32_t)n_chunks;
+            *vphase = ph;
 #ifdef FL_PROFILE
             if (pf.p && pf.trace_slot >= 0) pf.p[31] = gtimer();
 #endif
@@ -1050,10 +1165,11 @@ __device__ __forceinline__ void attention_part(const MegaParams& p, const SeqVie
     }
     pf.stop(tid, 15);
     if (!(p.debug_skip & 4)) consumer_sync();     // the other warps start polling for the next phase only now: their strong loads share the LSU with the PV warp's shared-memory loads
+    if (big && tid == 0) st_shared_volatile_u32(gate, gate_val);      // the ring is the producer's again
 }
 
 // ---------------------------------------------------------------------------------------------- the kernel
-template <int QT, int GS, int HS, bool MS = false, bool RX = false>
+template <int QT, int GS, int HS, bool MS = false, bool RX = false, bool LC = false>
 __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __grid_constant__ MegaParams p) {
     using RK = Rk<QT, GS>;
     const int n_seqs = MS ? p.n_seqs : 1;
@@ -1068,9 +1184,9 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
     if (tid == 0) {
         for (int i = 0; i < n_slots; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         uint64_t* vfull = reinterpret_cast<uint64_t*>(smem + p.off_vbars);
-        for (int i = 0; i < p.n_vchunks; ++i) mbar_init(&vfull[i], 1);
+        for (int i = 0; i < 32; ++i) mbar_init(&vfull[i], 1);
         *issued = 0u;
-        reinterpret_cast<uint32_t*>(smem + p.off_misc)[28] = 0u;
+        reinterpret_cast<uint32_t*>(smem + p.off_misc)[28] = 0u;      // V barrier phases
         reinterpret_cast<uint32_t*>(smem + p.off_misc)[24] = 0u;      // pair buffer 0 / 1: times released by the chain warp
         reinterpret_cast<uint32_t*>(smem + p.off_misc)[25] = 0u;
         reinterpret_cast<uint32_t*>(smem + p.off_misc)[31] = 0u;
@@ -1450,7 +1566,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
                 for (int sq = 0; sq < n_seqs; ++sq) {
                     const int pos = (MS ? sstate[4 * sq + 2] : pos0) + step;
                     const int bs = step == 0 ? (MS ? sstate[4 * sq + 3] : bs0) : 1;
-                    attention_part<HS, RX>(p, seq_view<MS>(p, sq), smem, layer, my_head, my_part, pos, bs, tl + 1u, tl + 2u, tl + 3u, phases_drained, tid, pf,
+                    attention_part<HS, RX, LC>(p, seq_view<MS>(p, sq), smem, layer, my_head, my_part, pos, bs, tl + 1u, tl + 2u, tl + 3u, phases_drained, tid, pf,
                                        MS ? nullptr : reinterpret_cast<uint32_t*>(smem + p.off_misc) + 20, (uint32_t)(step * n_phases + pi) + 2u);
                 }
             }

@@ -16,6 +16,8 @@ from fixtures import (ModelSpec, TINY, TINY64, gen_weights, quantize_model, prom
 pytestmark = pytest.mark.gpu
 
 GQA = ModelSpec(dim=512, hidden_dim=704, n_layers=2, n_heads=8, n_kv_heads=2, vocab_size=1000)
+# 40 heads of 128 (the 13B attention shape: 2 CTAs per head, 64 head dims each) over a thin FFN, so that the CPU oracle can walk a long context
+WIDE40 = ModelSpec(dim=5120, hidden_dim=1024, n_layers=1, n_heads=40, n_kv_heads=40, vocab_size=512)
 
 
 def make_port_model(spec, qm, qt, gs, max_seq=1024):
@@ -198,6 +200,9 @@ LONG_CASES = [
     ("tiny64-int8-330", TINY64, Q_INT8, 64, 330, 11),
     ("gqa-int8-200", GQA, Q_INT8, 64, 200, 12),
     ("tiny-int16-130", TINY, Q_INT16, 64, 130, 11),
+    # long contexts: V staged in the weight ring (more than twice the chunks of the small staging area), with refills of that ring too
+    ("tiny-int8-900", TINY, Q_INT8, 64, 900, 11),
+    ("wide40-g32-720", WIDE40, Q_INT8, 32, 720, 13),       # 13B head geometry, 32-wide groups (config 5's arithmetic); ~80 s of oracle time
 ]      # seeds chosen so that the oracle's greedy run does not hit the end token (id 0) before n_new
 
 
