@@ -212,6 +212,21 @@ __device__ __forceinline__ void st_relaxed_v4(uint4* p, uint4 v) {
     asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+// where the rmsnorm rebuild's sum-of-squares chain runs (A/B builds): 0 = on the chain warp, x * w under it; 1 = on the chain warp,
+// x * w in front of it; 2 = on consumer warp 7, x * w of the other warps under it
+#ifndef FL_RB_MODE
+#define FL_RB_MODE 0
+#endif
+constexpr int kRbMode = FL_RB_MODE;
+
+// sensitivity experiments (profiles/r02/delay_sensitivity.log): -DFL_DELAY_AT=n spins ~1 us at point n, else nothing
+template <int POINT>
+__device__ __forceinline__ void delay_point() {
+#ifdef FL_DELAY_AT
+    if (POINT == FL_DELAY_AT) { const long long t = clock64(); while (clock64() - t < 2000) { } }
+#endif
+}
+
 // per-CTA phase timing, only when MegaParams::prof is set; lives in registers.  Thread kProfThread keeps the clock.
 struct Prof {
     unsigned long long* p; unsigned long long t0; int trace_slot;   // trace_slot >= 0: the current build records when its input was complete
@@ -221,10 +236,17 @@ struct Prof {
 #endif
     }
     unsigned long long* ev;           // event log of this CTA while the traced layer runs, else NULL
+    static __device__ __forceinline__ unsigned long long evtime() {
+#ifdef FL_EVLOG_CLOCK      // SM cycles instead of %globaltimer (256 ns steps): events inside one CTA only
+        return (unsigned long long)clock64() & 0xffffffffffull;
+#else
+        return gtimer();
+#endif
+    }
     unsigned int* evn;                // its event counter (shared memory: a global atomic with a return value costs a round trip)
     __device__ __forceinline__ void log(int lane, int warp, int type, int arg) {
 #ifdef FL_EVLOG          // the per-warp event log is a debugging build: it costs ~10 KB of code the instruction cache needs
-        if (ev && lane == 0) { const unsigned int i = atomicAdd(evn, 1u); if (i < 4095u) ev[1 + i] = (gtimer() << 24) | ((unsigned long long)warp << 20) | ((unsigned long long)type << 12) | (unsigned long long)(arg & 0xfff); ev[0] = i + 1; }
+        if (ev && lane == 0) { const unsigned int i = atomicAdd(evn, 1u); if (i < 4095u) ev[1 + i] = (evtime() << 24) | ((unsigned long long)warp << 20) | ((unsigned long long)type << 12) | (unsigned long long)(arg & 0xfff); ev[0] = i + 1; }
 #endif
     }
     // absolute timestamp of one event of the traced layer (slots 22..31): skew and latency of one exchange, see profiles/trace_layer.py
@@ -467,7 +489,8 @@ __device__ __forceinline__ float sumsq_chain_t(const float* xt, int n, int lane)
 // profiles/r02/ab_chain_warp.log; the code is in the history, commit 777712b.)
 template <int QT, int GS, bool RX = false>
 __device__ __forceinline__ void build_activation(uint8_t* xq, float* xs, float* xt, float* misc, const uint2* src, uint32_t tag,
-                                                 const float* gain, int K, int n_prod, float* tap, int tid, Prof& pf, uint32_t* gate, uint32_t gate_val) {
+                                                 const float* gain, int K, int n_prod, float* tap, int tid, Prof& pf, uint32_t* gate, uint32_t gate_val,
+                                                 uint32_t chain_phases) {
     using RK = Rk<QT, GS>;
     constexpr int PER = GS / 8;                 // values per thread per group
     constexpr int LPP = PER / 2;                // 16-byte loads per thread per pass
@@ -504,16 +527,25 @@ __device__ __forceinline__ void build_activation(uint8_t* xq, float* xs, float* 
         }
     }
     float4 gw[MAXP][PER / 4];
-    if (gain) {
-        // the gain vector (16 KB per layer, L2-resident); measured: fetching it after the poll instead (fewer registers held
-        // across the poll) puts the products behind the chain and costs more than the spill of half of it does
+    auto load_gain = [&]() {
+        // the gain vector (16 KB per layer, L2-resident)
 #pragma unroll
         for (int ps = 0; ps < MAXP; ++ps) {
             const int g = min(g0 + ps * GPP, G - 1);        // clamped: always a valid address, unused where the thread has no group
 #pragma unroll
             for (int q = 0; q < PER / 4; ++q) gw[ps][q] = __ldg(reinterpret_cast<const float4*>(gain + g * GS + sub * PER) + q);
         }
-    }
+    };
+#if !defined(FL_OLD_REBUILD) && !defined(FL_GAIN_EARLY)
+    // rmsnorm rebuilds with the chain on the chain warp: x * w runs under the chain, so the gain is fetched only after the poll
+    // (its round trip hides under the chain as well, and its 24 registers are not held - and spilled - across the poll)
+    constexpr bool kGainLate = !RX && kRbMode == 0;
+#else
+    constexpr bool kGainLate = false;
+#endif
+    // otherwise before the poll; measured in round 1: fetching it after the poll puts the products behind the chain and costs
+    // more than the spill of half of it does
+    if (gain && !kGainLate) load_gain();
     bool again;
     do {
         again = false;
@@ -545,13 +577,37 @@ __device__ __forceinline__ void build_activation(uint8_t* xq, float* xs, float* 
     pf.stop(tid, 0);
     pf.log(tid & 31, tid >> 5, 9, 0);
     pf.mark(tid, pf.trace_slot, pf.trace_slot >= 0);
-    // every warp has left the previous phase (its drain / attention read the image this build overwrites)
-    consumer_sync();
-    // the input is here: the producer may prefetch again (measured: releasing later costs more ring prefetch than it saves in contention)
-    if (gate && tid == 0) st_shared_volatile_u32(gate, gate_val);
-    // zero the padded tail so padded groups contribute fma(0, 0, acc) == acc
-    for (int i = K * RK::ES + tid * 4; i < kpad_bytes; i += kConsumerThreads * 4) *reinterpret_cast<uint32_t*>(xq + i) = 0u;
-    for (int i = G + tid; i < (kpad_bytes / kStageRowBytes) * RK::GPS; i += kConsumerThreads) xs[i] = 0.0f;
+#ifndef FL_OLD_REBUILD
+    // rmsnorm rebuilds: the sum-of-squares chain runs on the CTA's chain warp (idle between two drains), and everything of
+    // the rebuild that does not need its result (x * w, the group maxima) runs under it.  A consumer thread that has its words
+    // stores the raw values into the transposed vector and ARRIVES on a named barrier (it does not wait); the chain warp waits
+    // there for all 256, opens the producer's gate, walks the chain and arrives on a second barrier the consumers wait on before
+    // the quantisation tail.  (Round 1/2a had the chain on consumer warp 7 between two consumer-wide barriers, with x * w and
+    // the maxima in front of it: 1.2 us more per rebuild on the critical path, profiles/r02/trace_rebuild_*.log.)
+    const bool chained = gain != nullptr && !RX;
+#else
+    const bool chained = false;
+#endif
+    if (chained) {
+        // xt lies on the pair buffers: this CTA's own chain warp must have finished the previous drain (it nearly always has:
+        // its rows are part of the vector just polled)
+        while ((int)(ld_shared_volatile_u32(reinterpret_cast<const uint32_t*>(misc) + 29) - chain_phases) < 0) __nanosleep(20);
+#ifdef FL_GATE_EARLY      // A/B: the first warp that has its words opens the gate (the others' last polls then share the memory system with the refill)
+        if (lane == 0 && gate) st_shared_volatile_u32(gate, gate_val);
+        if (tid == 0) st_shared_volatile_u32(reinterpret_cast<uint32_t*>(misc) + 19, 0u);
+#else
+        if (tid == 0) st_shared_volatile_u32(reinterpret_cast<uint32_t*>(misc) + 19, gate ? gate_val : 0u);       // the chain warp opens the gate
+#endif
+    } else {
+        // every warp has left the previous phase (its drain / attention read the image this build overwrites)
+        consumer_sync();
+        pf.log(lane, warp, 20, 0);
+        // the input is here: the producer may prefetch again (measured: releasing later costs more ring prefetch than it saves in contention)
+        if (gate && tid == 0) st_shared_volatile_u32(gate, gate_val);
+        // zero the padded tail so padded groups contribute fma(0, 0, acc) == acc
+        for (int i = K * RK::ES + tid * 4; i < kpad_bytes; i += kConsumerThreads * 4) *reinterpret_cast<uint32_t*>(xq + i) = 0u;
+        for (int i = G + tid; i < (kpad_bytes / kStageRowBytes) * RK::GPS; i += kConsumerThreads) xs[i] = 0.0f;
+    }
     // values out of the tagged words (the tags' registers are free from here on)
     float y[MAXP][PER];
     float ss_part = 0.0f;
@@ -578,26 +634,58 @@ __device__ __forceinline__ void build_activation(uint8_t* xq, float* xs, float* 
             }
         }
     }
-    // x*w and the group maxima while the chain is still to come (max |(x*w)*r| == (max |x*w|)*r: rounding is monotonic, r > 0)
+    // x*w and the group maxima (max |(x*w)*r| == (max |x*w|)*r: rounding is monotonic, r > 0)
     float m[MAXP];
+    auto pre = [&]() {
 #pragma unroll
-    for (int ps = 0; ps < MAXP; ++ps) {
-        const int g = g0 + ps * GPP;
-        float mm = 0.0f;
-        if (ps < n_pass && g < G) {
-            if (gain) {
+        for (int ps = 0; ps < MAXP; ++ps) {
+            const int g = g0 + ps * GPP;
+            float mm = 0.0f;
+            if (ps < n_pass && g < G) {
+                if (gain) {
 #pragma unroll
-                for (int q = 0; q < PER / 4; ++q) {                 // x*w, multiply_avx256 x86_simd.cpp:1359
-                    y[ps][4 * q] = __fmul_rn(y[ps][4 * q], gw[ps][q].x); y[ps][4 * q + 1] = __fmul_rn(y[ps][4 * q + 1], gw[ps][q].y);
-                    y[ps][4 * q + 2] = __fmul_rn(y[ps][4 * q + 2], gw[ps][q].z); y[ps][4 * q + 3] = __fmul_rn(y[ps][4 * q + 3], gw[ps][q].w);
+                    for (int q = 0; q < PER / 4; ++q) {                 // x*w, multiply_avx256 x86_simd.cpp:1359
+                        y[ps][4 * q] = __fmul_rn(y[ps][4 * q], gw[ps][q].x); y[ps][4 * q + 1] = __fmul_rn(y[ps][4 * q + 1], gw[ps][q].y);
+                        y[ps][4 * q + 2] = __fmul_rn(y[ps][4 * q + 2], gw[ps][q].z); y[ps][4 * q + 3] = __fmul_rn(y[ps][4 * q + 3], gw[ps][q].w);
+                    }
                 }
-            }
 #pragma unroll
-            for (int i = 0; i < PER; ++i) mm = fmaxf(mm, fabsf(y[ps][i]));
+                for (int i = 0; i < PER; ++i) mm = fmaxf(mm, fabsf(y[ps][i]));
+            }
+            m[ps] = group_max8(mm);
         }
-        m[ps] = group_max8(mm);
+    };
+    bool have_rr = false;
+    if (chained) {
+        delay_point<5>();
+        if (kRbMode == 0) {
+            asm volatile("bar.arrive 5, %0;" :: "n"(kConsumerThreads + 32) : "memory");       // my part of xt is written
+            pf.log(lane, warp, 20, 0);
+            if (kGainLate) load_gain();
+            pre();
+        } else if (kRbMode == 1) {
+            pre();
+            asm volatile("bar.arrive 5, %0;" :: "n"(kConsumerThreads + 32) : "memory");
+            pf.log(lane, warp, 20, 0);
+        } else if (warp == kSerialWarp) {
+            // mode 2: the chain stays on consumer warp 7 (alone on its sub-partition but for warp 3); its own x * w follows the chain
+            asm volatile("bar.sync 5, %0;" :: "n"(kConsumerThreads) : "memory");
+            if (lane == 0 && gate) st_shared_volatile_u32(gate, gate_val);
+            const float ss = sumsq_chain_t(xt, K, lane);
+            if (lane == 0) misc[18] = rms_scale(ss, K);
+            __syncwarp();
+            asm volatile("bar.arrive 6, %0;" :: "n"(kConsumerThreads) : "memory");
+            pre();
+            have_rr = true;
+        } else {
+            asm volatile("bar.arrive 5, %0;" :: "n"(kConsumerThreads) : "memory");
+            pre();
+        }
+    } else {
+        pre();
     }
     pf.stop(tid, 8);
+    pf.log(lane, warp, 21, 0);
     float rr = 1.0f;
     if (gain && RX) {
 #pragma unroll
@@ -608,16 +696,26 @@ __device__ __forceinline__ void build_activation(uint8_t* xq, float* xs, float* 
 #pragma unroll
         for (int w8 = 1; w8 < kConsumerWarps; ++w8) ss = __fadd_rn(ss, misc[8 + w8]);
         rr = rms_scale(ss, K);
+    } else if (chained) {
+        if (kRbMode != 2) asm volatile("bar.sync 6, %0;" :: "n"(kConsumerThreads + 32) : "memory");         // the chain warp has published the scale
+        else if (!have_rr) asm volatile("bar.sync 6, %0;" :: "n"(kConsumerThreads) : "memory");
+        rr = misc[18];
+        // every consumer warp is here, i.e. has left the previous phase: the image may be overwritten
+        for (int i = K * RK::ES + tid * 4; i < kpad_bytes; i += kConsumerThreads * 4) *reinterpret_cast<uint32_t*>(xq + i) = 0u;
+        for (int i = G + tid; i < (kpad_bytes / kStageRowBytes) * RK::GPS; i += kConsumerThreads) xs[i] = 0.0f;
     } else if (gain) {
         consumer_sync();
+        pf.log(lane, warp, 22, 0);
         if (warp == kSerialWarp) {
             const float ss = sumsq_chain_t(xt, K, lane);
+            pf.log(lane, warp, 23, 0);
             if (lane == 0) misc[18] = rms_scale(ss, K);
         }
         consumer_sync();
         rr = misc[18];
     }
     pf.stop(tid, 9);
+    pf.log(lane, warp, 24, 0);
 #pragma unroll
     for (int ps = 0; ps < MAXP; ++ps) {
         const int g = g0 + ps * GPP;
@@ -630,6 +728,8 @@ __device__ __forceinline__ void build_activation(uint8_t* xq, float* xs, float* 
             quant_store<QT, GS>(xq, xs, y[ps], m[ps], g, sub, tap);
         }
     }
+    pf.log(lane, warp, 25, 0);
+    if (chained) delay_point<1>();
     consumer_sync();
 }
 
@@ -1155,6 +1255,7 @@ __device__ __forceinline__ void attention_part(const MegaParams& p, const SeqVie
             if (n_chunks == 0) o = __fmul_rn(v, w);
             else if (fabsf(w) > 1e-15f) o = __fmaf_rn(v, w, o);
         }
+        delay_point<3>();
         st_tag(sv.attnt + (size_t)qh * HS + d0 + pvt, o, tag_out);
         if (pvt == 0) {
             *vphase = ph;
@@ -1299,6 +1400,23 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
                 const int gstride = (kPairGroups / ph.tt) * 32;          // float2s per sub-stream in a pair buffer
                 float best_v = -INFINITY;
                 int best_i = 0x7fffffff;
+#ifndef FL_OLD_REBUILD
+                if (kRbMode != 2 && !RX && (pk == 0 || pk == 2 || pk == 4) && !(p.debug_skip & 8)) {
+                    // the rmsnorm rebuild's sum of squares (build_activation): all 256 consumer threads have polled their words
+                    // and stored them into the transposed vector
+                    asm volatile("bar.sync 5, %0;" :: "n"(kConsumerThreads + 32) : "memory");
+                    float* misc = reinterpret_cast<float*>(smem + p.off_misc);
+                    if (lane == 0) {
+                        // the input is here: the producer may prefetch again
+                        const uint32_t gv = ld_shared_volatile_u32(reinterpret_cast<const uint32_t*>(misc) + 19);
+                        if (gv) st_shared_volatile_u32(reinterpret_cast<uint32_t*>(misc) + 20, gv);
+                    }
+                    const float ss = sumsq_chain_t(reinterpret_cast<const float*>(smem + p.off_xt), p.dim, lane);
+                    if (lane == 0) misc[18] = rms_scale(ss, p.dim);
+                    pf.log(lane, 9, 23, 0);
+                    asm volatile("bar.arrive 6, %0;" :: "n"(kConsumerThreads + 32) : "memory");
+                }
+#endif
 #pragma unroll 1
                 for (int t = 0; t < pt.nt; ++t) {
                     const int lr0 = pg[PG_LR + t], R = pg[PG_LR + t + 1] - lr0;
@@ -1337,6 +1455,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
                         if (lane == 0) st_shared_volatile_u32(freed + buf, (sbseq >> 1) + 1u);        // buffer released
                         ++sbseq;
                     }
+                    if (t == pt.nt - 1) delay_point<2>();
                     if (live) {
                         float v;
                         if (pk == 0 || pk == 4) v = acc;
@@ -1453,7 +1572,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
                 } else if (!(p.debug_skip & 8)) {
                     // producers of the vector: every CTA owns dim * c / n rows of x1; the attention parts own HS / cph outputs each
                     build_activation<QT, GS, RX>(xq, xs, xt, misc, in, tag_in, gain, K, (pk == 1) ? n_attn_ctas : (int)gridDim.x,
-                                                 (pk == 4 && blockIdx.x == 0) ? p.tap_norm : nullptr, tid, pf, (!MS && pk == 1) ? nullptr : gate, gate_val);
+                                                 (pk == 4 && blockIdx.x == 0) ? p.tap_norm : nullptr, tid, pf, (!MS && pk == 1) ? nullptr : gate, gate_val, phases_drained);
                 }
             }
             pf.stop(tid, 1);
