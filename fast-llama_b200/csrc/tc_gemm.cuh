@@ -140,14 +140,25 @@ __host__ __device__ constexpr uint32_t tc_idesc_i8(int M, int N) {
     return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 // descriptors travel as (lo, hi) halves: hi (stride offset, version) is constant, lo = start address | leading offset << 16
+// Called by ALL lanes of the issuer warp with warp-uniform operands; one elected lane issues.  The election lives inside
+// the asm so that the surrounding control flow stays warp-uniform: with the whole loop under `if (lane == 0)` (round 2, first
+// version) every operand was a per-lane value and the compiler wrapped each UTCIMMA in R2UR moves and an ELECT / BRA.U.ANY
+// waterfall loop - 116 cycles per MMA, 128-344 MMAs per CTA per matrix, i.e. most of a GEMM's run time at N = 8
+// (profiles/r02/ncu_full_r02_qgemm_decode8.csv: t = 12 us + 0.059 us x MMAs for all four matrices, tensor pipe 0.15 % active).
 template <bool ACC>
 __device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
         "setp.ne.b32 p, %5, 0;\n\t"
         "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %4, {%6, %6, %6, %6}, p;\n\t}"
+        "@e tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %4, {%6, %6, %6, %6}, p;\n\t}"
         :: "r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "n"(ACC ? 1 : 0), "r"(0u) : "memory");
+}
+// all tcgen05 operations the elected lane issued so far -> one arrival on `bar` (all lanes call, one commits)
+__device__ __forceinline__ void tc_commit_elect(uint64_t* bar) {
+    asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+                 "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" :: "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, int (&d)[16]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -284,7 +295,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) qgemm_kernel(const __grid_const
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
+        {
             const uint32_t idesc = tc_idesc_i8(128, N);
             const uint32_t desc_hi = (128u >> 4) | (1u << 14);       // stride (M/N) byte offset 128, descriptor version 1
             uint32_t slot = 0, par = 0, un = 0, upar = 1;            // tempty parity 1 passes on a fresh barrier
@@ -321,11 +332,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) qgemm_kernel(const __grid_const
                                     }
                                 }
                             }
-                            tc_commit(&tfull[un]);
+                            tc_commit_elect(&tfull[un]);
                             if (++un == (uint32_t)NUNITS) { un = 0; upar ^= 1u; }
                         }
                     }
-                    tc_commit(&empty[slot]);      // the stage's operands have been read once every MMA above has completed
+                    tc_commit_elect(&empty[slot]);      // the stage's operands have been read once every MMA above has completed
                     if (++slot == (uint32_t)n_slots) { slot = 0; par ^= 1u; }
                 }
             }

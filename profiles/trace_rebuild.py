@@ -40,3 +40,11 @@ for which, name in ((0, "CTA 7 (attention)"), (1, "CTA n-3")):
             names = {10: "buf", 1: "wait", 2: "ready", 3: "done", 4: "sb?", 5: "sb!", 6: "ROWS"}
             st = [f"{names[typ[i]]}@{(t[i] - ts) / MHZ:.2f}" for i in order if warp[i] == w and ts <= t[i] <= te + 10 * MHZ and typ[i] in names]
             if st: print(f"  warp {w} drain events: " + " ".join(st[:16]))
+        if pk == 0:
+            # attention follows the QKV drain: QKV_IN = q/k/v polled, SCORES = own scores done, SOFTMAX = scores exchanged, ATTN_OUT = softmax done (PV follows)
+            an = {16: "QKV_IN", 13: "SCORES", 14: "SOFTMAX", 15: "ATTN_OUT", 11: "v?", 12: "v!"}
+            for w in range(8):
+                st = [f"{an[typ[i]]}@{(t[i] - ts) / MHZ:.2f}" for i in order if warp[i] == w and ts <= t[i] <= ts + 40 * MHZ and typ[i] in an]
+                if st: print(f"  warp {w} attention: " + " ".join(st[:12]))
+            nb = [(t[i] - ts) / MHZ for i in order if typ[i] == 8 and warp[i] == 0 and t[i] > ts]
+            if nb: print(f"  next build (Wo) starts at {nb[0]:.2f}")
