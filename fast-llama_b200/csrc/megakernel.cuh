@@ -572,7 +572,10 @@ __device__ __forceinline__ void build_activation(uint8_t* xq, float* xs, float* 
         }
         // a poll that failed is not worth repeating at once: the LSU is shared with warps still working (measured again in
         // round 2: no sleep 427.8 against 431.0 tokens/s)
-        if (again) __nanosleep(100);
+#ifndef FL_SENT_SLEEP
+#define FL_SENT_SLEEP 30       // a sentinel round is 9 sectors per warp: a short back-off is enough (30 vs 100 ns: 492.9 vs 490.9 tokens/s, profiles/r02/ab_sentinel_sleep.log)
+#endif
+        if (again) __nanosleep(use_sentinel ? FL_SENT_SLEEP : 100);
     } while (again);
     pf.stop(tid, 0);
     pf.log(tid & 31, tid >> 5, 9, 0);
