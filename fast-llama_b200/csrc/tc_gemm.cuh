@@ -296,7 +296,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) qgemm_kernel(const __grid_const
     } else if (warp == 1) {
         // ================= MMA issuer =================
         {
-            const uint32_t idesc = tc_idesc_i8(128, N);
+            // M = 64 where the CTA's tiles have at most 64 rows (Wo, W2: 28-35 rows per CTA): the MMA reads half the A rows from
+            // shared memory.  Measured: no change (8 sequences 3.01 vs 2.96 ms per step, profiles/r02/rows_bench_v3.log) - the
+            // ~95 cycles per K = 32 MMA are not the A read
+            const uint32_t idesc = tc_idesc_i8(r_max <= 64 ? 64 : 128, N);
             const uint32_t desc_hi = (128u >> 4) | (1u << 14);       // stride (M/N) byte offset 128, descriptor version 1
             uint32_t slot = 0, par = 0, un = 0, upar = 1;            // tempty parity 1 passes on a fresh barrier
             for (int t = 0; t < pt.nt; ++t) {
@@ -345,7 +348,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) qgemm_kernel(const __grid_const
         // ================= epilogue: the FP32 chain over groups, one weight row per thread =================
         const int ew = warp - 2, wg = ew >> 2;
         const int q = warp & 3;                                  // the TMEM lane quadrant this warp may read
-        const int r = q * 32 + lane;                             // local row inside the tile
+        // accumulator row -> TMEM lane: M = 128: row i in lane i; M = 64: row i in lane (i % 16) + 32 * (i / 16), i.e. the first
+        // 16 lanes of every quadrant (cute/atom/mma_traits_sm100.hpp, half-subpartition atom)
+        const int rpq = r_max <= 64 ? 16 : 32;                   // rows per quadrant
+        const int r = q * rpq + lane;                            // local row inside the tile
         const int c0 = DUAL ? 0 : (SPLIT ? wg * NC : 0);         // first activation row of this thread
         const int msel = DUAL ? wg : 0;                          // which matrix of the fused stream
         const uint32_t tcol = (uint32_t)(DUAL ? wg * N : c0);
@@ -354,8 +360,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) qgemm_kernel(const __grid_const
         for (int t = 0; t < pt.nt; ++t) {
             int lr0, R;
             tc_tile(pt, t, lr0, R);
-            const bool quad_live = q * 32 < R;
-            const bool live = r < R;
+            const bool quad_live = q * rpq < R;
+            const bool live = lane < rpq && r < R;
             const int row = pt.rb + lr0 + r;
             float acc[NC];
 #pragma unroll
