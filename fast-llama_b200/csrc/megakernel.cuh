@@ -174,6 +174,19 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// One ring stage issued by the producer WARP: all lanes call with warp-uniform operands, one elected lane arms the barrier, starts
+// the bulk copy and publishes the new issue count with a release store (ordered after the arming).  With the loop under
+// `if (lane == 0)` the compiler wrapped every UBLKCP in five R2UR.BROADCAST moves and an ELECT / BRA.U.ANY waterfall loop and the
+// count needed a MEMBAR.SC.CTA: ~180 cycles per stage, i.e. 2 us to request a ring refill after the gate opens.
+__device__ __forceinline__ void issue_stage_elect(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint32_t* issued, uint32_t count) {
+#ifndef FL_OLD_PRODUCER
+    asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+                 "@e mbarrier.arrive.expect_tx.shared::cta.b64 _, [%3], %2;\n\t"
+                 "@e cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t"
+                 "@e st.release.cta.shared.u32 [%4], %5;\n\t}"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "r"(smem_u32(issued)), "r"(count) : "memory");
+#endif
+}
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" :: "n"(kConsumerThreads) : "memory"); }
 __device__ __forceinline__ unsigned long long gtimer() {
     unsigned long long t;
@@ -1315,7 +1328,11 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
 
     if (warp == kConsumerWarps) {
         // ================= TMA producer =================
+#ifdef FL_OLD_PRODUCER
         if (lane == 0) {
+#else
+        {       // the whole warp walks the schedule (warp-uniform control flow), one elected lane issues: see issue_stage_elect
+#endif
             uint32_t sc = 0, slot = 0, par = 1;         // empty[] parity to wait for: 1 passes on a fresh barrier
             // In-flight window: stage i is issued only after stage i - window has LANDED.  The ring is deep so that it can
             // buffer microseconds of weights, but requests queued in the memory system are pure latency for everyone else
@@ -1357,10 +1374,14 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
                                 if (++wslot == (uint32_t)n_slots) { wslot = 0; wpar ^= 1u; }
                             }
                             mbar_wait_sleep(&empty[slot], par);
+#ifdef FL_OLD_PRODUCER
                             mbar_arrive_expect_tx(&full[slot], bytes);
                             bulk_g2s(ring + (size_t)slot * p.slot_bytes, src, bytes, &full[slot]);
                             __threadfence_block();                      // the barrier is armed before the count says so
                             st_shared_volatile_u32(issued, ++sc);
+#else
+                            issue_stage_elect(ring + (size_t)slot * p.slot_bytes, src, bytes, &full[slot], issued, ++sc);
+#endif
                             src += bytes;
                             if (++slot == (uint32_t)n_slots) { slot = 0; par ^= 1u; }
                         }
