@@ -585,6 +585,12 @@ __device__ __forceinline__ void build_activation(uint8_t* xq, float* xs, float* 
         }
         // a poll that failed is not worth repeating at once: the LSU is shared with warps still working (measured again in
         // round 2: no sleep 427.8 against 431.0 tokens/s)
+#ifndef FL_ISSUED_SLEEP
+#define FL_ISSUED_SLEEP 40
+#endif
+#ifndef FL_GATE_SLEEP
+#define FL_GATE_SLEEP 64
+#endif
 #ifndef FL_SENT_SLEEP
 #define FL_SENT_SLEEP 30       // a sentinel round is 9 sectors per warp: a short back-off is enough (30 vs 100 ns: 492.9 vs 490.9 tokens/s, profiles/r02/ab_sentinel_sleep.log)
 #endif
@@ -1353,7 +1359,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
                     if (!MS && !(p.debug_skip & (8 | 32))) {
                         const uint32_t need = (uint32_t)(step * n_phases + pi) + 1u;
                         const uint32_t* gate = reinterpret_cast<const uint32_t*>(smem + p.off_misc) + 20;
-                        while ((int)(ld_shared_volatile_u32(gate) - need) < 0) __nanosleep(64);
+                        while ((int)(ld_shared_volatile_u32(gate) - need) < 0) __nanosleep(FL_GATE_SLEEP);
                     }
 #pragma unroll 1
                     for (int sq = 0; sq < n_seqs; ++sq) {
@@ -1361,7 +1367,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
                         // several sequences: every (phase, sequence) pass is released by that sequence's own poll
                         const uint32_t need = (uint32_t)((step * n_phases + pi) * n_seqs + sq) + 1u;
                         const uint32_t* gate = reinterpret_cast<const uint32_t*>(smem + p.off_misc) + 20;
-                        while ((int)(ld_shared_volatile_u32(gate) - need) < 0) __nanosleep(64);
+                        while ((int)(ld_shared_volatile_u32(gate) - need) < 0) __nanosleep(FL_GATE_SLEEP);
                     }
                     const uint8_t* src = reinterpret_cast<const uint8_t* const*>(smem + p.off_psrc)[pi];      // the stream is laid out in issue order
 #pragma unroll 1
@@ -1637,7 +1643,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_megakernel(const __gri
 #pragma unroll 1
                             for (int m = 0; m < ph.tt; ++m) {
                                 pf.log(lane, warp, 1, (int)rel + m);
-                                while ((int)(ld_shared_volatile_u32(issued) - (sc + rel + (uint32_t)m)) <= 0) __nanosleep(40);      // fact 4 in the header
+                                while ((int)(ld_shared_volatile_u32(issued) - (sc + rel + (uint32_t)m)) <= 0) __nanosleep(FL_ISSUED_SLEEP);      // fact 4 in the header
                                 mbar_wait(&full[sl], pr);
                                 pf.stop(tid, (sc + rel + (uint32_t)m - drain_sc0 < 16u) ? 21 : 7);       // waiting for weights = the stream is the limit (21: the stages prefetched during the stall)
                                 pf.log(lane, warp, 2, (int)rel + m);

@@ -171,6 +171,10 @@ __device__ __forceinline__ void tc_ld8(uint32_t taddr, int (&d)[8]) {
                  : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7])
                  : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tc_ld4(uint32_t taddr, int (&d)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]) : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // programmatic dependent launch
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
@@ -201,7 +205,10 @@ struct TcShape {
     static constexpr int GU = (128 / NB) >= GPS ? GPS : ((128 / NB) >= 1 ? (128 / NB) : 1);     // groups per TMEM unit (<= 128 columns)
     static constexpr int UPS = GPS / GU;                   // units per stage
     static constexpr int NUNITS = (512 / (GU * NB)) > 8 ? 8 : (512 / (GU * NB));
-    static constexpr bool SPLIT = !DUAL && N >= 16;        // the two epilogue warpgroups share the columns of one accumulator
+    // the two epilogue warpgroups share the columns of one accumulator.  Also at N = 8 (4 columns each): the epilogue is one
+    // latency-bound instruction stream per live TMEM quadrant (28 rows = one warp), and it - not the MMA issue (halving the
+    // MMAs: 3.05 -> 2.89 ms per step) nor the weight stream - paces the thin GEMMs at ~0.65 us per stage
+    static constexpr bool SPLIT = !DUAL;
     static constexpr int NC = (DUAL || !SPLIT) ? N : N / 2;   // columns (activation rows) per epilogue thread
     static constexpr int EPW = (DUAL || SPLIT) ? 8 : 4;    // epilogue warps that take part
     static_assert(GPS % GU == 0 && NUNITS >= 2, "unit geometry");
@@ -330,7 +337,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) qgemm_kernel(const __grid_const
                                             const uint32_t a_lo = (a_img + (uint32_t)m * (kTcKC / 16) * lbo_a + k16 * lbo_a) | (lbo_a << 16);
                                             const uint32_t b_lo = (b_img + k16 * lbo_b) | (lbo_b << 16);
                                             if (k32 == 0) tc_mma_i8<false>(dcol, a_lo, b_lo, desc_hi, idesc);
+#ifndef FL_TC_SKIP_HALF        // timing experiment (wrong results): is the GEMM bound by the MMA issue?
                                             else tc_mma_i8<true>(dcol, a_lo, b_lo, desc_hi, idesc);
+#endif
                                         }
                                     }
                                 }
@@ -379,7 +388,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) qgemm_kernel(const __grid_const
                         tc_fence_after();
                         if (quad_live) {
                             const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + un * (GU * NB) + tcol;
-                            if (NC == 8) {
+                            if constexpr (NC == 4) {
+                                int d[GU][4];
+#pragma unroll
+                                for (int gg = 0; gg < GU; ++gg) tc_ld4(tbase + (uint32_t)(gg * NB), d[gg]);
+                                tc_ld_wait();
+#pragma unroll
+                                for (int gg = 0; gg < GU; ++gg) {
+                                    const int g = u * GU + gg;
+                                    if (g < ng) {
+                                        const float ws = live ? ws_st[g * R + r] : 0.0f;
+                                        const float4 x0 = *reinterpret_cast<const float4*>(xs_st + g * N + c0);
+                                        const float xs[4] = {x0.x, x0.y, x0.z, x0.w};
+#pragma unroll
+                                        for (int i = 0; i < 4; ++i) acc[i] = __fmaf_rn(__fmul_rn(ws, xs[i]), __int2float_rn(d[gg][i]), acc[i]);
+                                    }
+                                }
+                            } else if constexpr (NC == 8) {
                                 // all groups of the unit at once: GU x 8 columns, NB columns apart
                                 int d[GU][8];
 #pragma unroll
