@@ -13,6 +13,9 @@ What is taken over from the converter, quirks included (they decide the bytes of
   * tensors in checkpoint order (`_dump_tensors`, :1109-1172): q_proj / k_proj rows permuted for the interleaved RoPE
     (`permute_qk`), every 2-D tensor except the embedding quantised with numpy float32 arithmetic and C truncation, group 64
     (the converter hard-codes 64 whatever -g says, :1111); 1-D tensors and the embedding stay fp32.
+    Byte identity with the converter holds for FP32 checkpoints (what the tests cover): every tensor is widened to float32
+    before quantisation here, while `TensorLoader.quantize` (:216-243) works in the checkpoint's own dtype, so for an fp16
+    (HalfStorage) checkpoint its max / 127 and division happen in float16 and payload and scales can differ from this path.
 Only single-file PyTorch checkpoints (pytorch_model.bin / *.pt / consolidated.00.pth) are read, via torch.load."""
 import json
 import os
