@@ -166,7 +166,6 @@ struct AttnRowsArgs {
 // RoPE(k) + KV append of every row (transformer.cpp:431-439).  grid (n_kv_heads, T), HS threads.
 template <int HS>
 __global__ void __launch_bounds__(HS) kv_append_rows_kernel(const AttnRowsArgs a) {
-    constexpr int EPL = HS / 8;
     pdl_launch_dependents();
     pdl_wait();
     const int kvh = blockIdx.x, i = blockIdx.y, tid = threadIdx.x;
@@ -181,8 +180,8 @@ __global__ void __launch_bounds__(HS) kv_append_rows_kernel(const AttnRowsArgs a
         float o0, o1;
         rope_pair(cs.x, cs.y, x.x, x.y, o0, o1);
         float* krow = kc + (size_t)rm.pos * HS;
-        krow[((2 * tid) & 7) * EPL + ((2 * tid) >> 3)] = o0;
-        krow[((2 * tid + 1) & 7) * EPL + ((2 * tid + 1) >> 3)] = o1;
+        krow[k_cache_index(2 * tid)] = o0;
+        krow[k_cache_index(2 * tid + 1)] = o1;
         if (a.tap_qkv && i == a.tap_row) { a.tap_qkv[dim + (size_t)kvh * HS + 2 * tid] = o0; a.tap_qkv[dim + (size_t)kvh * HS + 2 * tid + 1] = o1; }
     } else {
         const int d = 2 * (tid - HS / 2);
@@ -238,9 +237,9 @@ __global__ void __launch_bounds__(kThreads) attn_rows_kernel(const AttnRowsArgs 
             for (int u = 0; u < U; ++u) {
                 const int t = base + (u * kWarps + warp) * 4 + rr;
                 if (t < n) {
-                    const float4* p = reinterpret_cast<const float4*>(kc + (size_t)t * HS + j * EPL);
+                    const float4* p = reinterpret_cast<const float4*>(kc + (size_t)t * HS) + j;
 #pragma unroll
-                    for (int c = 0; c < EPL / 4; ++c) kv[u][c] = __ldcg(p + c);
+                    for (int c = 0; c < EPL / 4; ++c) kv[u][c] = __ldcg(p + 8 * c);
                 } else {
 #pragma unroll
                     for (int c = 0; c < EPL / 4; ++c) kv[u][c] = make_float4(0.f, 0.f, 0.f, 0.f);

@@ -1724,7 +1724,7 @@ int fl_op_attn_decode(int n_heads, int n_kv_heads, int head_size, int pos, const
         for (int h = 0; h < n_kv_heads; ++h) {
             if (k_new) {
                 CKO(cudaMemcpy(row.data(), dk.as<float>() + ((size_t)h * max_seq + pos) * hs, (size_t)hs * 4, cudaMemcpyDeviceToHost));
-                for (int e2 = 0; e2 < hs; ++e2) k_new[(size_t)h * hs + e2] = row[(e2 & 7) * (hs / 8) + (e2 >> 3)];
+                for (int e2 = 0; e2 < hs; ++e2) k_new[(size_t)h * hs + e2] = row[k_cache_index(e2)];
             }
             if (v_new) CKO(cudaMemcpy(v_new + (size_t)h * hs, dv.as<float>() + ((size_t)h * max_seq + pos) * hs, (size_t)hs * 4, cudaMemcpyDeviceToHost));
         }

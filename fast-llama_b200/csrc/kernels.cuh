@@ -131,6 +131,12 @@ __device__ __forceinline__ float sumsq_chain_warp0(const float* xf, int n, int l
 }
 
 // r = 1/sqrtf(ss/n + 1e-5f)   (x86_simd.cpp:1755 as compiled: vdivss, vaddss, vsqrtss, vdivss)
+// K cache row layout.  A row is read by 8 lanes, lane j walking the reference's AVX lane j (elements 8 i + j, i ascending: the
+// order of its FMA chain).  Lane j's q-th float4 (i = 4q .. 4q + 3) lives at float4 index 8 q + j, so the 8 lanes of a row read
+// 128 contiguous bytes per load: coalesced from global memory, conflict-free from the shared-memory ring of the long-context
+// attention (round 2; before, lane j's 16 values were contiguous: 4-way bank conflicts once K rows were staged unpadded).
+__host__ __device__ __forceinline__ int k_cache_index(int e) { const int j = e & 7, i = e >> 3; return (((i >> 2) << 3) + j) * 4 + (i & 3); }
+
 __device__ __forceinline__ float rms_scale(float ss, int n) {
     return __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(__fdiv_rn(ss, (float)n), 1e-5f)));
 }
@@ -402,8 +408,8 @@ __global__ void embed_kernel(const float* __restrict__ table, const int* __restr
 
 // ---------------------------------------------------------------------------------------------
 // Attention for one new token — execute_attn (transformer.cpp:397-455).  One CTA per query head.
-//   K cache row layout: lane-permuted for the reference's 8-lane AVX2 dot (x86_simd.cpp:1447-1468):
-//     float j*(HS/8) + i  <-  k[8*i + j]      (lane j's FMA chain is contiguous: HS/8 floats)
+//   K cache row layout: lane-permuted for the reference's 8-lane AVX2 dot (x86_simd.cpp:1447-1468), see k_cache_index:
+//     float ((i / 4) * 8 + j) * 4 + i % 4  <-  k[8*i + j]      (lane j's q-th float4 at float4 index 8 q + j)
 //   V cache row layout: natural.
 // ---------------------------------------------------------------------------------------------
 struct AttnArgs {
@@ -485,8 +491,8 @@ __global__ void __launch_bounds__(kThreads) attn_decode_kernel(const AttnArgs a)
         k_s[2 * i] = o0; k_s[2 * i + 1] = o1;
         if (g == 0) {
             float* krow = kc + (size_t)pos * HS;
-            krow[((2 * i) & 7) * EPL + ((2 * i) >> 3)] = o0;
-            krow[((2 * i + 1) & 7) * EPL + ((2 * i + 1) >> 3)] = o1;
+            krow[k_cache_index(2 * i)] = o0;
+            krow[k_cache_index(2 * i + 1)] = o1;
             if (a.tap_qkv) { a.tap_qkv[dim + (size_t)kvh * HS + 2 * i] = o0; a.tap_qkv[dim + (size_t)kvh * HS + 2 * i + 1] = o1; }
         }
     } else if (tid < HS + HS / 4) {
@@ -513,9 +519,9 @@ __global__ void __launch_bounds__(kThreads) attn_decode_kernel(const AttnArgs a)
             for (int u = 0; u < U; ++u) {
                 const int t = base + (u * kWarps + warp) * 4 + rr;
                 if (t < pos) {
-                    const float4* p = reinterpret_cast<const float4*>(kc + (size_t)t * HS + j * EPL);
+                    const float4* p = reinterpret_cast<const float4*>(kc + (size_t)t * HS) + j;
 #pragma unroll
-                    for (int c = 0; c < EPL / 4; ++c) kv[u][c] = __ldcg(p + c);
+                    for (int c = 0; c < EPL / 4; ++c) kv[u][c] = __ldcg(p + 8 * c);
                 } else if (t == pos) {
 #pragma unroll
                     for (int c = 0; c < EPL / 4; ++c)
@@ -716,10 +722,9 @@ __global__ void __launch_bounds__(kThreads) op_softmax_kernel(const float* x, in
 
 // natural-order K rows -> lane-permuted cache rows (per-op attention entry point / tests)
 __global__ void permute_k_rows_kernel(const float* src, float* dst, int rows, int hs) {
-    const int epl = hs / 8;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rows * hs; i += gridDim.x * blockDim.x) {
         const int row = i / hs, e = i % hs;
-        dst[(size_t)row * hs + (e & 7) * epl + (e >> 3)] = src[i];
+        dst[(size_t)row * hs + k_cache_index(e)] = src[i];
     }
 }
 

@@ -893,7 +893,7 @@ template <int HS>
 __device__ __forceinline__ KSweepOut k_sweep_ring(float* kring, uint64_t* vfull, uint32_t* kprog, const float* kc, const float* q_s, const float* k_s,
                                                float* att, uint2* att_g, int tb, int kc_end, int te, int pos, int NKC, int nkch, int cph,
                                                float attn_scale, uint32_t tag_score, uint32_t ph, int tid) {
-    constexpr int EPL = HS / 8, KR = 32, KROW = HS + 4;
+    constexpr int EPL = HS / 8, KR = 32, KROW = HS;       // unpadded rows: a chunk of 32 rows is ONE 16 KB bulk copy (4-way bank conflicts on the reads are cheaper than 32 copies)
     const int warp = tid >> 5, lane = tid & 31, rr = lane >> 3, j = lane & 7;
     float mloc = -INFINITY;
     const float* qj = q_s + j;
@@ -918,9 +918,11 @@ __device__ __forceinline__ KSweepOut k_sweep_ring(float* kring, uint64_t* vfull,
     };
     auto issue_k = [&](int c) {                             // warp 0, all lanes (same as attention_part's)
         const int slot = c % NKC, t0 = tb + c * KR, rows = min(KR, kc_end - t0);
-        if (lane == 0) mbar_arrive_expect_tx(&vfull[slot], (uint32_t)(rows * HS * 4));
+        if (lane == 0) {
+            mbar_arrive_expect_tx(&vfull[slot], (uint32_t)(rows * HS * 4));
+            bulk_g2s(kring + (size_t)slot * KR * KROW, kc + (size_t)t0 * HS, (uint32_t)(rows * HS * 4), &vfull[slot]);
+        }
         __syncwarp();
-        if (lane < rows) bulk_g2s(kring + ((size_t)slot * KR + lane) * KROW, kc + (size_t)(t0 + lane) * HS, HS * 4, &vfull[slot]);
     };
 #pragma unroll 1
     for (int c = 0; c < nkch; ++c) {
@@ -928,10 +930,10 @@ __device__ __forceinline__ KSweepOut k_sweep_ring(float* kring, uint64_t* vfull,
         mbar_wait(&vfull[slot], (ph >> slot) & 1u);
         ph ^= 1u << slot;
         const int t = tb + c * KR + warp * 4 + rr;
-        const float4* kp = reinterpret_cast<const float4*>(kring + ((size_t)slot * KR + warp * 4 + rr) * KROW + j * EPL);
+        const float4* kp = reinterpret_cast<const float4*>(kring + ((size_t)slot * KR + warp * 4 + rr) * KROW) + j;      // k_cache_index: conflict-free
         float4 k4[EPL / 4];
 #pragma unroll
-        for (int q = 0; q < EPL / 4; ++q) k4[q] = (t < kc_end) ? kp[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int q = 0; q < EPL / 4; ++q) k4[q] = (t < kc_end) ? kp[8 * q] : make_float4(0.f, 0.f, 0.f, 0.f);
         score(k4, t, t < kc_end);
         __syncwarp();
         if (lane == 0) st_shared_volatile_u32(kprog + warp, (uint32_t)c + 1u);
@@ -987,16 +989,23 @@ __device__ __forceinline__ void attention_part(const MegaParams& p, const SeqVie
     // opens after PV (Wo's 2.4 us of prefetch are noise next to a 10-30 us sweep).  Needs the gate: not in multi-sequence launches.
     // LC: the long-context code exists only in the kernel variant the host launches when a sequence can get that far (its
     // registers and instructions would otherwise tax the short-context path: +430 bytes of spills in the phase loop)
-    const bool big = LC && gate != nullptr && n_chunks > 2 * p.n_vchunks;
+    // (the host launches the LC variant only for a single sequence that is already past 2 * n_vchunks chunks: launch_mega)
+    constexpr bool big = LC;
 #ifdef FL_LONG_K
+    // A/B build: K through the ring as well - chunks of 32 rows = ONE 16 KB bulk copy each (the cache keeps a head's rows
+    // contiguous), ~10 chunks in flight
     constexpr bool kRingK = true;
 #else
-    // measured (profiles/r02/longctx_ab.log): with K through the ring as well the 13B long-context case ran at 106.6 tokens/s
-    // against 138.8 with K in registers - one 512-byte bulk copy per row (the padded row stride needs them) is too fine a
-    // grain for the copy engine; the code stays for the A/B build
+    // Measured at the 13B shape from context 2048 / 7B from 900 (profiles/r02/longctx_k_ring.log, longctx_k_layout.log):
+    //   register-staged K, lane j's 16 values contiguous in the row (round 1 layout) ............ 152.0 / 404.6 tokens/s
+    //   K through the ring, one 512-byte copy per row into padded rows (32-lane ELECT waterfall) . 107   (longctx_ab.log)
+    //   K through the ring, one 16 KB copy per chunk, unpadded rows (4-way bank conflicts) ....... 161.4 / 411.1
+    //   new row layout (k_cache_index: a row's 8 lanes read 128 contiguous bytes), ring .......... 169.9 / 422.2
+    //   new row layout, register-staged K ....................................................... 172.7 / 431.0   <- default
+    // The register sweep had been slow because each LDG.128 of a warp touched 32 separate 16-byte pieces 64 bytes apart.
     constexpr bool kRingK = false;
 #endif
-    const bool bigk = big && kRingK;
+    constexpr bool bigk = big && kRingK;
     float* v_stage = reinterpret_cast<float*>(smem + (big ? p.off_ring : p.off_vstage));
     const int NCH = big ? min(32, (p.n_slots * p.slot_bytes) / (VR * DW * 4)) : p.n_vchunks;
     auto issue_v = [&](int c) {                             // one thread
@@ -1027,9 +1036,10 @@ __device__ __forceinline__ void attention_part(const MegaParams& p, const SeqVie
     const int tb = part * per, te = min(n, tb + per);
     const int rr = lane >> 3, j = lane & 7;
     // long contexts: the part's cached K rows [tb, min(te, pos)) stream through the weight ring as well (before V, which is
-    // requested once the sweep is over): chunks of 32 rows, one 512-byte bulk copy per row into a row stride of HS * 4 + 16
-    // bytes (conflict-free LDS.128 for 4 keys x 8 lanes), NKC chunks in flight instead of one register batch per round trip
-    constexpr int KR = 32, KROW = HS + 4;                   // rows per K chunk; floats per staged row
+    // requested once the sweep is over): chunks of 32 contiguous rows, one bulk copy each (the unpadded rows cost 4-way bank
+    // conflicts on the LDS.128 of 4 keys x 8 lanes - cheaper than 32 copies), NKC chunks in flight instead of one register
+    // batch per round trip
+    constexpr int KR = 32, KROW = HS;                       // rows per K chunk; floats per staged row (unpadded: one bulk copy per chunk)
     const int kc_end = min(te, pos);
     const int nkch = bigk ? ceil_div(max(kc_end - tb, 0), KR) : 0;
     const int NKC = bigk ? min(32, (p.n_slots * p.slot_bytes) / (KR * KROW * 4)) : 1;
@@ -1037,9 +1047,11 @@ __device__ __forceinline__ void attention_part(const MegaParams& p, const SeqVie
     uint32_t* kprog = reinterpret_cast<uint32_t*>(smem + p.off_misc) + 416;     // [warp] K chunks this warp has finished
     auto issue_k = [&](int c) {                             // warp 0, all lanes
         const int slot = c % NKC, t0 = tb + c * KR, rows = min(KR, kc_end - t0);
-        if (lane == 0) mbar_arrive_expect_tx(&vfull[slot], (uint32_t)(rows * HS * 4));
+        if (lane == 0) {
+            mbar_arrive_expect_tx(&vfull[slot], (uint32_t)(rows * HS * 4));
+            bulk_g2s(kring + (size_t)slot * KR * KROW, kc + (size_t)t0 * HS, (uint32_t)(rows * HS * 4), &vfull[slot]);
+        }
         __syncwarp();
-        if (lane < rows) bulk_g2s(kring + ((size_t)slot * KR + lane) * KROW, kc + (size_t)(t0 + lane) * HS, HS * 4, &vfull[slot]);
     };
     if (bigk) {
         if (lane == 0) kprog[warp] = 0u;
@@ -1056,16 +1068,16 @@ __device__ __forceinline__ void attention_part(const MegaParams& p, const SeqVie
         for (int u = 0; u < UU; ++u) {
             const int t = base + (u * kConsumerWarps + warp) * 4 + rr;
             if (t < pos && t < te) {
-                const float4* kp = reinterpret_cast<const float4*>(kc + (size_t)t * HS + j * EPL);
+                const float4* kp = reinterpret_cast<const float4*>(kc + (size_t)t * HS) + j;
 #pragma unroll
-                for (int q = 0; q < EPL / 4; ++q) kv[u][q] = __ldcg(kp + q);
+                for (int q = 0; q < EPL / 4; ++q) kv[u][q] = __ldcg(kp + 8 * q);
             } else {
 #pragma unroll
                 for (int q = 0; q < EPL / 4; ++q) kv[u][q] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
     };
-    if (!bigk) load_k(tb);
+    if constexpr (!bigk) load_k(tb);
 
     // ---- q, k, v rows of this head: 3 * HS tagged words, one 16-byte load (= one RoPE pair) per thread
     // RoPE + KV append (rope_v2 tf_operators.cpp:355-402; transformer.cpp:431-439)
@@ -1088,8 +1100,8 @@ __device__ __forceinline__ void attention_part(const MegaParams& p, const SeqVie
             k_s[2 * i] = o0; k_s[2 * i + 1] = o1;
             if (g == 0 && part == 0) {
                 float* krow = kc + (size_t)pos * HS;
-                krow[((2 * i) & 7) * EPL + ((2 * i) >> 3)] = o0;
-                krow[((2 * i + 1) & 7) * EPL + ((2 * i + 1) >> 3)] = o1;
+                krow[k_cache_index(2 * i)] = o0;
+                krow[k_cache_index(2 * i + 1)] = o1;
             }
         } else {
             v_s[2 * i] = x0; v_s[2 * i + 1] = x1;
@@ -1107,7 +1119,7 @@ __device__ __forceinline__ void attention_part(const MegaParams& p, const SeqVie
     // ---- scores for this part's keys: float dot_product_avx256 (x86_simd.cpp:1447-1468): 8 FMA chains, then 0 + l0 + ... + l7
     uint2* att_g = sv.score_t + (size_t)qh * p.score_stride;
     float mloc = -INFINITY;                        // running maximum of the scores this thread stores (softmax's max, fused)
-    if (bigk) {
+    if constexpr (bigk) {
         const KSweepOut ko = k_sweep_ring<HS>(kring, vfull, kprog, kc, q_s, k_s, att, att_g, tb, kc_end, te, pos, NKC, nkch, cph, p.attn_scale, tag_score, ph, tid);
         ph = ko.ph; mloc = ko.mloc;
     } else {

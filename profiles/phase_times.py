@@ -1,4 +1,5 @@
-"""Per-category time inside the persistent decode kernel (FL_FLAG_PROFILE), LLaMA2-7B-shaped INT8."""
+"""Per-category time inside the persistent decode kernel (FL_FLAG_PROFILE): phase_times.py [ctx] [steps] [7b | 13b]
+(7b = LLaMA2-7B-shaped INT8 group 64; 13b = LLaMA2-13B-shaped INT8 group 32 = Q8_0 arithmetic)."""
 import os, sys
 os.environ.setdefault('FL_PROF_LIB', '1')     # the library build with the profiling counters compiled in
 import numpy as np
@@ -7,11 +8,17 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import __graft_entry__ as ge
 from bench import synth_int8_model, shape_7b
 fl = ge._pkg()
-spec = shape_7b()
 ctx = int(sys.argv[1]) if len(sys.argv) > 1 else 288
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 64
-eng = fl.Engine(spec.dim, spec.hidden_dim, spec.n_layers, spec.n_heads, spec.n_kv_heads, spec.vocab_size, max_seq_len=1024, flags=fl.FLAG_PROFILE)
-for (kind, layer), (q, s) in synth_int8_model(spec, 0):
+big = len(sys.argv) > 3 and sys.argv[3] == "13b"
+if big:
+    from fixtures import LLAMA2_13B
+    spec, gs = LLAMA2_13B, 32
+else:
+    spec, gs = shape_7b(), 64
+max_seq = max(1024, (ctx + steps + 8 + 3) // 4 * 4)
+eng = fl.Engine(spec.dim, spec.hidden_dim, spec.n_layers, spec.n_heads, spec.n_kv_heads, spec.vocab_size, max_seq_len=max_seq, group_size=gs, flags=fl.FLAG_PROFILE)
+for (kind, layer), (q, s) in synth_int8_model(spec, 0, gs=gs):
     eng.upload(kind, layer, q, s)
 eng.finalize()
 tok = np.array([5], np.int32)
