@@ -403,29 +403,54 @@ __device__ __forceinline__ float group_max8(float m) {
 
 // quantise one lane's share of a group (PER consecutive values, 8 lanes per group) given the group's max |value|:
 // quant::quantize (quant_operators.cpp:26-47); packed and stored as words.
+// Which values of a 64-wide (32-wide) quantisation group one of its 8 lanes owns.  Interleaved (default): the lane's q-th pair
+// of values is the pair 8 q + sub of the group, so the 8 lanes of a group read 128 contiguous bytes of tagged words per load
+// and a warp's LDG.128 covers whole 32-byte sectors.  (Round 1 gave a lane 8 consecutive values = 64 contiguous bytes: its
+// four loads each touched half a sector, i.e. every sector of an exchanged vector crossed the L2 -> SM fabric twice.)
+#ifndef FL_NO_POLL_IL
+constexpr bool kPollIL = true;
+#else
+constexpr bool kPollIL = false;
+#endif
+template <int GS>
+__device__ __forceinline__ int lane_elem(int sub, int q) { return kPollIL ? 16 * q + 2 * sub : sub * (GS / 8) + 2 * q; }      // first of the pair, inside the group
+
 template <int QT, int GS>
 __device__ __forceinline__ void quant_store(uint8_t* xq, float* xs, const float (&y)[GS / 8], float m, int g, int sub, float* tap) {
     constexpr int PER = GS / 8;
     const float QF = (QT == Q_INT8) ? 127.0f : 5792.0f;
     const float sc = __fdiv_rn(m, QF);
     if (sub == 0) xs[g] = sc;
-    const int e0 = g * GS + sub * PER;
-    constexpr int EPW = (QT == Q_INT8) ? 4 : 2;            // elements per 32-bit word
-    uint32_t pk[PER / EPW];
+    uint32_t qv[PER];
 #pragma unroll
     for (int i = 0; i < PER; ++i) {
         // (T)(y / sc) with a true IEEE division, inlined.  Measured alternatives, both slower: a reciprocal-multiply fast path
         // with a fallback near integers (some lane nearly always needs the fallback), and a non-inlined helper per value / per
         // 4 values (the calls cost more than the instruction-cache space they save).
-        const uint32_t q = (uint32_t)cvtt_x86(__fdiv_rn(y[i], sc)) & ((QT == Q_INT8) ? 0xffu : 0xffffu);
-        pk[i / EPW] = (i % EPW == 0) ? q : (pk[i / EPW] | (q << ((32 / EPW) * (i % EPW))));
+        qv[i] = (uint32_t)cvtt_x86(__fdiv_rn(y[i], sc)) & ((QT == Q_INT8) ? 0xffu : 0xffffu);
     }
-    uint32_t* dst = reinterpret_cast<uint32_t*>(xq + (size_t)e0 * ((QT == Q_INT8) ? 1 : 2));     // natural element order
+    if constexpr (kPollIL) {
+        // pairs of consecutive elements: 16-bit (INT8) / 32-bit (INT16) stores, natural element order
 #pragma unroll
-    for (int i = 0; i < PER / EPW; ++i) dst[i] = pk[i];
-    if (tap) {
+        for (int q = 0; q < PER / 2; ++q) {
+            const int e = g * GS + lane_elem<GS>(sub, q);
+            if (QT == Q_INT8) *reinterpret_cast<uint16_t*>(xq + e) = (uint16_t)(qv[2 * q] | (qv[2 * q + 1] << 8));
+            else *reinterpret_cast<uint32_t*>(xq + (size_t)e * 2) = qv[2 * q] | (qv[2 * q + 1] << 16);
+            if (tap) { tap[e] = y[2 * q]; tap[e + 1] = y[2 * q + 1]; }
+        }
+    } else {
+        const int e0 = g * GS + sub * PER;
+        constexpr int EPW = (QT == Q_INT8) ? 4 : 2;            // elements per 32-bit word
+        uint32_t pk[PER / EPW];
 #pragma unroll
-        for (int i = 0; i < PER; ++i) tap[e0 + i] = y[i];
+        for (int i = 0; i < PER; ++i) pk[i / EPW] = (i % EPW == 0) ? qv[i] : (pk[i / EPW] | (qv[i] << ((32 / EPW) * (i % EPW))));
+        uint32_t* dst = reinterpret_cast<uint32_t*>(xq + (size_t)e0 * ((QT == Q_INT8) ? 1 : 2));     // natural element order
+#pragma unroll
+        for (int i = 0; i < PER / EPW; ++i) dst[i] = pk[i];
+        if (tap) {
+#pragma unroll
+            for (int i = 0; i < PER; ++i) tap[e0 + i] = y[i];
+        }
     }
 }
 
@@ -518,7 +543,7 @@ __device__ __forceinline__ void build_activation(uint8_t* xq, float* xs, float* 
     uint2 sv[MAXP];                             // the sentinel of each pass
     const float rows_per_prod = (float)K / (float)n_prod, prod_per_row = (float)n_prod / (float)K;
     auto sentinel = [&](int ps) {
-        const int last = (g0 + ps * GPP) * GS + sub * PER + PER - 1;                    // my last word of the pass
+        const int last = (g0 + ps * GPP) * GS + lane_elem<GS>(sub, LPP - 1) + 1;        // my last word of the pass
         const int c = (int)((float)(last + 1) * prod_per_row);                           // ~ its producer
         return max(last, min(K - 1, (int)((float)(c + 1) * rows_per_prod) - 1));         // ~ that producer's last row
     };
@@ -533,20 +558,20 @@ __device__ __forceinline__ void build_activation(uint8_t* xq, float* xs, float* 
         if (ps < n_pass && g < G) {
             if (use_sentinel) sv[ps] = ld_tag1(src + sentinel(ps));
             else {
-                const uint2* s = src + g * GS + sub * PER;
+                const uint2* s = src + g * GS;
 #pragma unroll
-                for (int q = 0; q < LPP; ++q) w[ps][q] = ld_tag2(s + 2 * q);
+                for (int q = 0; q < LPP; ++q) w[ps][q] = ld_tag2(s + lane_elem<GS>(sub, q));
             }
         }
     }
-    float4 gw[MAXP][PER / 4];
+    float2 gw[MAXP][LPP];
     auto load_gain = [&]() {
         // the gain vector (16 KB per layer, L2-resident)
 #pragma unroll
         for (int ps = 0; ps < MAXP; ++ps) {
             const int g = min(g0 + ps * GPP, G - 1);        // clamped: always a valid address, unused where the thread has no group
 #pragma unroll
-            for (int q = 0; q < PER / 4; ++q) gw[ps][q] = __ldg(reinterpret_cast<const float4*>(gain + g * GS + sub * PER) + q);
+            for (int q = 0; q < LPP; ++q) gw[ps][q] = __ldg(reinterpret_cast<const float2*>(gain + g * GS + lane_elem<GS>(sub, q)));
         }
     };
 #if !defined(FL_OLD_REBUILD) && !defined(FL_GAIN_EARLY)
@@ -566,11 +591,11 @@ __device__ __forceinline__ void build_activation(uint8_t* xq, float* xs, float* 
         for (int ps = 0; ps < MAXP; ++ps) {
             const int g = g0 + ps * GPP;
             if (ps < n_pass && g < G) {
-                const uint2* s = src + g * GS + sub * PER;
+                const uint2* s = src + g * GS;
                 if (!((loaded >> ps) & 1u)) {
                     if (sv[ps].y == tag) {
 #pragma unroll
-                        for (int q = 0; q < LPP; ++q) w[ps][q] = ld_tag2(s + 2 * q);
+                        for (int q = 0; q < LPP; ++q) w[ps][q] = ld_tag2(s + lane_elem<GS>(sub, q));
                         loaded |= 1u << ps;
                     } else {
                         sv[ps] = ld_tag1(src + sentinel(ps));
@@ -579,7 +604,7 @@ __device__ __forceinline__ void build_activation(uint8_t* xq, float* xs, float* 
                 } else {
 #pragma unroll
                     for (int q = 0; q < LPP; ++q)
-                        if (w[ps][q].y != tag || w[ps][q].w != tag) { w[ps][q] = ld_tag2(s + 2 * q); again = true; }
+                        if (w[ps][q].y != tag || w[ps][q].w != tag) { w[ps][q] = ld_tag2(s + lane_elem<GS>(sub, q)); again = true; }
                 }
             }
         }
@@ -644,14 +669,23 @@ __device__ __forceinline__ void build_activation(uint8_t* xq, float* xs, float* 
                 for (int i = 0; i < PER; ++i) ss_part = __fmaf_rn(y[ps][i], y[ps][i], ss_part);
             }
             if (gain && !RX) {
-                // raw x -> transposed vector for the chain on the serial warp
-                const int e0 = g * GS + sub * PER;                   // multiple of 4
-                if constexpr (PER == 8) {
+                // raw x -> transposed vector for the chain (xt[j * K/4 + i] = x[4 i + j])
+                if constexpr (kPollIL) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) *reinterpret_cast<float2*>(xt + j * (K >> 2) + (e0 >> 2)) = make_float2(y[ps][j], y[ps][4 + j]);
+                    for (int q = 0; q < LPP; ++q) {
+                        const int e = g * GS + lane_elem<GS>(sub, q);           // even
+                        float* d = xt + (e & 3) * (K >> 2) + (e >> 2);
+                        d[0] = y[ps][2 * q]; d[K >> 2] = y[ps][2 * q + 1];
+                    }
                 } else {
+                    const int e0 = g * GS + sub * PER;                   // multiple of 4
+                    if constexpr (PER == 8) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) xt[j * (K >> 2) + (e0 >> 2)] = y[ps][j];
+                        for (int j = 0; j < 4; ++j) *reinterpret_cast<float2*>(xt + j * (K >> 2) + (e0 >> 2)) = make_float2(y[ps][j], y[ps][4 + j]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) xt[j * (K >> 2) + (e0 >> 2)] = y[ps][j];
+                    }
                 }
             }
         }
@@ -666,9 +700,8 @@ __device__ __forceinline__ void build_activation(uint8_t* xq, float* xs, float* 
             if (ps < n_pass && g < G) {
                 if (gain) {
 #pragma unroll
-                    for (int q = 0; q < PER / 4; ++q) {                 // x*w, multiply_avx256 x86_simd.cpp:1359
-                        y[ps][4 * q] = __fmul_rn(y[ps][4 * q], gw[ps][q].x); y[ps][4 * q + 1] = __fmul_rn(y[ps][4 * q + 1], gw[ps][q].y);
-                        y[ps][4 * q + 2] = __fmul_rn(y[ps][4 * q + 2], gw[ps][q].z); y[ps][4 * q + 3] = __fmul_rn(y[ps][4 * q + 3], gw[ps][q].w);
+                    for (int q = 0; q < LPP; ++q) {                     // x*w, multiply_avx256 x86_simd.cpp:1359
+                        y[ps][2 * q] = __fmul_rn(y[ps][2 * q], gw[ps][q].x); y[ps][2 * q + 1] = __fmul_rn(y[ps][2 * q + 1], gw[ps][q].y);
                     }
                 }
 #pragma unroll
