@@ -413,7 +413,7 @@ def run_single(args, local_rank):
                 "scope": f"decode_megakernel, ONE persistent launch = {n_dec} tokens (every phase of every layer of every token); algorithmic "
                          f"bytes per token = INT8 weights + fp32 group scales + fp32 KV read/write at mean ctx {mean_ctx:.0f} = {step_bytes / 1e9:.3f} GB "
                          "(SURVEY 8d); achieved = bytes per token / measured time per token (CUDA events on the engine stream)",
-                "traffic": 7.349e9, "traffic_note": "dram read 7.331 GB + write 0.018 GB per token from ncu --set full of a 1-token launch at ctx 288 (profiles/r02/ncu_full_r02_mega_7b_int8.csv)",
+                "traffic": 7.350e9, "traffic_note": "dram read 7.332 GB + write 0.018 GB per token from ncu --set full of a 1-token launch at ctx 288 (profiles/r02/ncu_full_r02_mega_7b_int8_final.csv; L2 -> SM 8.69 GB: 7.18 GB of bulk copies + 1.5 GB of polls and K rows)",
                 "peak_source": peak_src, "frac_of_8TBs": achieved / 8000.0}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
