@@ -29,7 +29,9 @@ if seqs == 1:
 else:
     for i in range(seqs):
         eng.forward(np.array([1 + i], np.int32), ctx - 2, slot=i, want_logits=False)
-    eng.decode_batch_async(seqs, launches)
+    toks = np.arange(1, seqs + 1, dtype=np.int32)
+    for k in range(launches):       # fl_forward_batch: one persistent launch (MS = true) advances every sequence by one token
+        toks = eng.forward_batch(toks, np.full(seqs, ctx - 1 + k, np.int32))
 eng.sync()
 print("done", name, ctx, launches)
 eng.close()
