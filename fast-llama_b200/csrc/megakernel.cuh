@@ -413,7 +413,7 @@ constexpr bool kPollIL = true;
 constexpr bool kPollIL = false;
 #endif
 template <int GS>
-__device__ __forceinline__ int lane_elem(int sub, int q) { return kPollIL ? 16 * q + 2 * sub : sub * (GS / 8) + 2 * q; }      // first of the pair, inside the group
+__host__ __device__ __forceinline__ int lane_elem(int sub, int q) { return kPollIL ? 16 * q + 2 * sub : sub * (GS / 8) + 2 * q; }      // first of the pair, inside the group
 
 template <int QT, int GS>
 __device__ __forceinline__ void quant_store(uint8_t* xq, float* xs, const float (&y)[GS / 8], float m, int g, int sub, float* tap) {
